@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""Benchmark of the hydrodynamic body-force path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # B200 arm (this repo's CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...   # reference arm: the CPU path on host cores
+
+metric  = body-force updates/s (whole job, all ranks)
+step    = one fused pass of the hot path over one resident batch of bodies
+workload (N=1) = BASELINE config "1M heterogeneous boxes per GPU" (C3): 2^20 bodies per GPU,
+          per-body coefficient records, fp32 mode, all force terms enabled.  The engine cycles
+          through several independent resident batches so that consecutive steps never find
+          their inputs in the 126 MB L2 (each batch is 176 MB of algorithmic traffic).
+One JSON line on stdout (rank 0).  Multi-GPU: one process per GPU under torchrun, env-sharded,
+no data-path collective; time = max over ranks of CUDA-event time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "body-force updates/sec"
+UNIT = "bodies/s"
+BYTES_PER_BODY_F32 = 168  # 19 state reads + 11 coefficient reads + 12 writes, fp32
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--bodies-per-gpu", type=int, default=1 << 20)
+    ap.add_argument("--batches", type=int, default=6, help="independent resident batches cycled through")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "tile", "direct"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C2/C5/fp64 side measurements")
+    ap.add_argument("--cpu-sample", type=int, default=1 << 20)
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the bench runs."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.stop_flag, self.ok = [], set(), False, False
+        self.sm_max = None
+        self.load_from = None
+
+    def run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+                getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+            }
+            self.ok = True
+            while not self.stop_flag:
+                t = time.perf_counter()
+                clk = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((t, clk))
+                if self.load_from is not None and t >= self.load_from:
+                    for bit, name in names.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                time.sleep(self.period)
+        except Exception as exc:  # NVML unavailable: report that instead of inventing clocks
+            self.error = repr(exc)
+
+    def summary(self, t0, t1):
+        under = [c for (t, c) in self.samples if t0 <= t <= t1]
+        if not self.ok or not under:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                    "note": getattr(self, "error", "no NVML samples inside the load window")}
+        return {"sm_mhz": float(np.median(under)), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(under)}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# --------------------------------------------------------------------------------------------
+def cpu_baseline(sample_bodies, min_seconds=10.0, max_reps=200):
+    """The oracle port (oracle/hydro_oracle.c, OpenMP over bodies) on the box's host cores."""
+    from oracle import hydro_oracle as O
+    from silver2_isaacsim_b200 import workloads as W
+
+    wl = W.heterogeneous_boxes(sample_bodies)
+    args = (wl.ctor_rows(), wl.masses(), wl.pos.astype(np.float64), wl.quat_xyzw.astype(np.float64),
+            wl.lin_vel.astype(np.float64), wl.ang_vel.astype(np.float64), wl.prev_lin.astype(np.float64),
+            wl.prev_ang.astype(np.float64), wl.dt)
+    O.step(*args)  # warm-up (page faults, OpenMP pool)
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        O.step(*args)
+        reps += 1
+        el = time.perf_counter() - t0
+        if (el >= min_seconds and reps >= 3) or reps >= max_reps:
+            break
+    return {"value": sample_bodies * reps / el, "unit": UNIT, "cores": O.max_threads(), "kind": "port",
+            "sample": f"{reps} passes over {sample_bodies} C3 bodies ({el:.1f} s), float64, "
+                      f"C restatement of the Numba path + behaviour tail, OpenMP"}
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path (oracle port; the reference
+    itself is Python/Numba and cannot travel to the box), all host threads, same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import hydro_oracle as O
+    from silver2_isaacsim_b200 import workloads as W
+
+    sample = min(args.bodies_per_gpu, 1 << 18)
+    wl = W.heterogeneous_boxes(sample)
+    a = (wl.ctor_rows(), wl.masses(), wl.pos.astype(np.float64), wl.quat_xyzw.astype(np.float64),
+         wl.lin_vel.astype(np.float64), wl.ang_vel.astype(np.float64), wl.prev_lin.astype(np.float64),
+         wl.prev_ang.astype(np.float64), wl.dt)
+    steps = max(1, min(args.steps, 400))
+    for _ in range(max(1, min(args.warmup, 5))):
+        O.step(*a)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.step(*a)
+    el = time.perf_counter() - t0
+    value = sample * steps / el
+    cores = O.max_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C3: heterogeneous boxes, per-body coefficient records, fused behaviour step",
+                   "bodies_per_step": sample, "host_threads": cores},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{steps} steps x {sample} C3 bodies, oracle/hydro_oracle.c with OpenMP"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+def make_batches(torch, W, n, n_batches, dtype, dev, seed0):
+    """Independent resident batches of the C3 workload (state tensors per batch; one engine each)."""
+    from silver2_isaacsim_b200 import HydroEngine
+
+    batches = []
+    npdt = np.float32 if dtype == torch.float32 else np.float64
+    for b in range(n_batches):
+        wl = W.heterogeneous_boxes(n, seed=seed0 + b, dtype=np.float32)
+        eng = HydroEngine(n, dtype=dtype, device=dev)
+        eng.set_workload_params(wl)
+        t = lambda a: torch.as_tensor(np.ascontiguousarray(a.astype(npdt)), device=dev)
+        eng.set_prev(t(wl.prev_lin), t(wl.prev_ang))
+        F, T = eng.bind(t(wl.pos), t(wl.quat_xyzw), t(wl.lin_vel), t(wl.ang_vel))
+        batches.append((eng, wl, F, T))
+    return batches
+
+
+def time_steps(torch, sharding, batches, steps, dt, dev):
+    """K fused steps, CUDA events on the launch stream, barrier + synchronize on both sides."""
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nb = len(batches)
+    torch.cuda.synchronize(dev)
+    sharding.barrier()
+    torch.cuda.synchronize(dev)
+    l0 = sum(b[0].launch_count for b in batches)
+    w0 = time.perf_counter()
+    ev0.record()
+    for i in range(steps):
+        batches[i % nb][0].step_bound(dt)
+    ev1.record()
+    torch.cuda.synchronize(dev)
+    w1 = time.perf_counter()
+    sharding.barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = sum(b[0].launch_count for b in batches) - l0
+    return ms, launches, (w0, w1)
+
+
+def side_measurements(torch, W, dev, dtype_main):
+    """C2 (hexapod x 4096, table + robot wrench), C5 (graph vs per-step launch), fp64 C3."""
+    from silver2_isaacsim_b200 import HydroEngine
+
+    out = {}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def bound_engine(wl, dtype, robot):
+        npdt = np.float32 if dtype == torch.float32 else np.float64
+        e = HydroEngine(wl.n, dtype=dtype, device=dev)
+        e.set_workload_params(wl)
+        t = lambda a: torch.as_tensor(np.ascontiguousarray(a.astype(npdt)), device=dev)
+        e.set_prev(t(wl.prev_lin), t(wl.prev_ang))
+        e.bind(t(wl.pos), t(wl.quat_xyzw), t(wl.lin_vel), t(wl.ang_vel), robot_wrench=robot)
+        return e
+
+    def timeit(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        ev0.record()
+        for _ in range(reps):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        return ev0.elapsed_time(ev1) / reps
+
+    # C2: 4096 envs x 19 bodies, part-type table in shared memory, per-robot wrench
+    wl = W.hexapod_envs(4096)
+    e = bound_engine(wl, torch.float32, True)
+    ms = timeit(lambda: e.step_bound(wl.dt), 200)
+    out["c2_hexapod_4096_envs"] = {"bodies": wl.n, "us_per_step": 1e3 * ms, "updates_per_s": wl.n / (ms * 1e-3),
+                                   "kernel": e.last_kernel, "note": "L2-resident (9.7 MB), launch-latency bound"}
+    # C5: 1024 bodies, 1000-step rollout: per-step launches vs one captured CUDA graph
+    wl5 = W.uniform_small_batch(1024)
+    e5 = bound_engine(wl5, torch.float32, False)
+    ms_eager = timeit(lambda: [e5.step_bound(wl5.dt) for _ in range(1000)], 3)
+    e5.capture_rollout(1000, wl5.dt)
+    ms_graph = timeit(e5.launch_rollout, 3)
+    out["c5_small_batch_1024x1000"] = {"us_per_step_launch": ms_eager, "us_per_step_graph": ms_graph,
+                                       "ratio": ms_eager / ms_graph, "state": "static (force-only rollout)"}
+    # fp64 mode on the C3 workload (336 B/body)
+    if dtype_main == torch.float32:
+        n = 1 << 20
+        bs = make_batches(torch, W, n, 3, torch.float64, dev, W.SEED_BASE + 300)
+        k = [0]
+
+        def f():
+            bs[k[0] % 3][0].step_bound(bs[0][1].dt)
+            k[0] += 1
+        ms64 = timeit(f, 60)
+        out["c3_fp64_mode"] = {"bodies": n, "us_per_step": 1e3 * ms64, "updates_per_s": n / (ms64 * 1e-3),
+                               "achieved_gbs": 2 * BYTES_PER_BODY_F32 * n / (ms64 * 1e-3) / 1e9}
+        del bs
+    return out
+
+
+def run_b200(args):
+    import torch
+
+    from silver2_isaacsim_b200 import sharding
+    from silver2_isaacsim_b200 import workloads as W
+
+    rank, world, local = sharding.init_distributed()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (b200 arm) needs a GPU: the engine has no CPU path")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    dtype = torch.float32 if args.dtype == "f32" else torch.float64
+    n = args.bodies_per_gpu
+    bpb = BYTES_PER_BODY_F32 * (1 if dtype == torch.float32 else 2)
+
+    batches = make_batches(torch, W, n, args.batches, dtype, dev, W.SEED_BASE + 3 + 1000 * rank)
+    for b in batches:
+        b[0].set_kernel(args.kernel)
+    dt = batches[0][1].dt
+
+    sampler = ClockSampler(physical_gpu_index(local)) if rank == 0 else None
+    if sampler:
+        sampler.start()
+
+    warm = max(3, args.warmup)
+    for i in range(warm):
+        batches[i % len(batches)][0].step_bound(dt)
+    torch.cuda.synchronize(dev)
+    # clock soak: ~1.2 s of the same kernel so that the NVML samples are taken under this load
+    if sampler:
+        sampler.load_from = time.perf_counter()
+    soak_t0 = time.perf_counter()
+    while time.perf_counter() - soak_t0 < 1.2:
+        for i in range(200):
+            batches[i % len(batches)][0].step_bound(dt)
+        torch.cuda.synchronize(dev)
+    ms, launches, (w0, w1) = time_steps(torch, sharding, batches, args.steps, dt, dev)
+    load_t1 = time.perf_counter()
+    ms_max = sharding.max_over_ranks(ms, dev)
+    total_bodies = sharding.sum_over_ranks(float(n), dev)
+    value = total_bodies * args.steps / (ms_max * 1e-3)
+
+    # roofline of the dominant (only) kernel: algorithmic bytes per launch / average launch time
+    per_launch_s = ms * 1e-3 / args.steps
+    achieved = bpb * n / per_launch_s / 1e9
+    peak, peak_src = measured_peak()
+    traffic = ncu_traffic()
+
+    # e2e: public API with HOST buffers (pinned), H2D + kernel + D2H inside the timed region
+    eng, wl, _, _ = batches[0]
+    npdt = np.float32 if dtype == torch.float32 else np.float64
+    pin = [torch.as_tensor(np.ascontiguousarray(a.astype(npdt))).pin_memory()
+           for a in (wl.pos, wl.quat_xyzw, wl.lin_vel, wl.ang_vel)]
+    oF = torch.empty(n, 3, dtype=dtype).pin_memory()
+    oT = torch.empty(n, 3, dtype=dtype).pin_memory()
+    e2e_steps = max(5, min(args.steps, 40))
+    for _ in range(3):
+        eng.step_host(*pin, dt, out_force=oF, out_torque=oT)
+    torch.cuda.synchronize(dev)
+    sharding.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.step_host(*pin, dt, out_force=oF, out_torque=oT)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    sharding.barrier()
+    e2e_s = sharding.max_over_ranks(e2e_s, dev)
+    esz = 4 if dtype == torch.float32 else 8
+    e2e = {"value": total_bodies * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * 13 * esz * world),
+           "d2h_bytes_per_step": int(n * 6 * esz * world), "steps": e2e_steps,
+           "api": "HydroEngine.step_host (h2o_step_host): pinned host buffers in/out, chunked 3-stream pipeline"}
+
+    # optional global statistics: the only collective (outside the timed region)
+    eng.enable_stats(True)
+    eng.step_bound(dt)
+    gstats = sharding.allreduce_stats(eng.stats_tensor())
+    eng.enable_stats(False)
+
+    clocks = None
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+        clocks = sampler.summary(soak_t0, load_t1)
+
+    extra = {}
+    if rank == 0 and not args.no_extra:
+        try:
+            extra = side_measurements(torch, W, dev, dtype)
+        except Exception as exc:  # side numbers must never lose the headline line
+            extra = {"error": repr(exc)}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args.cpu_sample)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "C3: 1M heterogeneous boxes per GPU (randomised dimensions/coefficients), "
+                                   "per-body coefficient records, fused step, all force terms",
+                       "bodies_per_gpu": n, "resident_batches": args.batches, "kernel": batches[0][0].last_kernel,
+                       "l2": f"inputs larger than L2: {args.batches} independent batches x "
+                             f"{bpb * n / 1e6:.0f} MB cycled, no flush needed",
+                       "parallelism": f"env-sharded x{world}, no data-path collective"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+                         "algorithmic_bytes_per_body": bpb, "bodies_per_launch": n,
+                         "frac_of_nominal_8TBs": achieved / 8000.0},
+            "e2e": e2e, "gpu_launches": int(launches * world), "clocks": clocks,
+            "cpu_baseline": cpu, "global_stats": gstats, "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,186 @@
+/*
+ * h2o.h -- C ABI of the B200-native hydrodynamics force engine (libh2o_b200.so).
+ *
+ * Drop-in boundary for ONE path of Joagai23/silver2_isaacsim: the per-body, per-step
+ * hydrodynamic force/torque evaluation.  Every entry point names the reference
+ * interface it replaces (paths relative to /root/reference/src/scripts/physics/).
+ *
+ * Conventions
+ *   - plain C: opaque handle, raw device pointers + sizes (or DLPack DLTensor*, see
+ *     h2o_dlpack.h); no C++/torch types cross the boundary.
+ *   - every function returns an h2o_status (0 = ok) and never throws;
+ *     h2o_last_error() returns a thread-local message for the last failure.
+ *   - all tensors are caller-owned, contiguous row-major, dtype == handle dtype,
+ *     on the handle's device, 16-byte aligned.  The engine borrows them for the
+ *     duration of the call (or until h2o_unbind for bound tensors) and never frees them.
+ *     The engine owns only: coefficient records, previous-step velocities, statistics,
+ *     captured graphs and pinned staging buffers.
+ *   - every launch takes an explicit cudaStream_t (pass torch.cuda.current_stream().cuda_stream);
+ *     there are no hidden synchronisations on the step path.
+ *   - a handle is not re-entrant: one caller thread at a time
+ *     (the reference is called serially from the PhysX step callback,
+ *     hydrodynamics_behavior.py:131-141).
+ */
+#ifndef H2O_H_
+#define H2O_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define H2O_API __attribute__((visibility("default")))
+#else
+#define H2O_API
+#endif
+
+typedef struct h2o_engine* h2o_handle;
+typedef void* h2o_stream; /* cudaStream_t */
+
+typedef enum {
+    H2O_OK = 0,
+    H2O_ERR_BAD_HANDLE = 1,
+    H2O_ERR_BAD_ARGUMENT = 2,
+    H2O_ERR_BAD_SHAPE = 3,
+    H2O_ERR_BAD_DTYPE = 4,
+    H2O_ERR_BAD_DEVICE = 5,
+    H2O_ERR_NOT_CONTIGUOUS = 6,
+    H2O_ERR_ALIGNMENT = 7,
+    H2O_ERR_NOT_CONFIGURED = 8, /* parameters / bound tensors / rollout missing */
+    H2O_ERR_CUDA = 9,
+    H2O_ERR_NO_DEVICE = 10
+} h2o_status;
+
+typedef enum { H2O_F32 = 0, H2O_F64 = 1 } h2o_dtype;
+typedef enum { H2O_QUAT_XYZW = 0, H2O_QUAT_WXYZ = 1 } h2o_quat_order;
+typedef enum { H2O_KERNEL_AUTO = 0, H2O_KERNEL_TILE = 1, H2O_KERNEL_DIRECT = 2 } h2o_kernel_choice;
+
+/* Number of scalars in one coefficient record and their order:
+ * xDimension, yDimension, zDimension, linearDragCoefficient, angularDragCoefficient,
+ * linearDamping, angularDamping, linearAddedMassCoefficient, angularAddedMassCoefficient,
+ * liftCoefficient, mass      (names: hydrodynamics_behavior.py:28-46; mass: :172-173) */
+#define H2O_N_COEFF 11
+/* h2o_stats vector: sum|F|, max|F|, wet bodies, clamped bodies, non-finite forces,
+ * wet-and-at-rest bodies (the reference raises there, numba_hydrodynamics.py:118,143),
+ * bodies processed, reserved. */
+#define H2O_N_STATS 8
+
+H2O_API const char* h2o_last_error(void);
+H2O_API const char* h2o_version(void);
+/* Number of CUDA devices visible, or a negative h2o_status. */
+H2O_API int h2o_device_count(void);
+
+/* ---- construction -------------------------------------------------------------------
+ * Replaces XHydrodynamicsWrapper.__init__ (numba_hydrodynamics_wrapper.py:9-32,
+ * warp_hydrodynamics_wrapper.py:10-77), batched over n_bodies, and
+ * HydrodynamicsBehavior._setup (hydrodynamics_behavior.py:143-174). */
+H2O_API int h2o_create(h2o_handle* out, int64_t n_bodies, int dtype, int device);
+H2O_API int h2o_destroy(h2o_handle h);
+
+/* waterDensity, gravity (hydrodynamics_behavior.py:30-31; hydrodynamics_config.json "globals") */
+H2O_API int h2o_set_globals(h2o_handle h, double water_density, double gravity);
+
+/* Same twelve scalars, same order as the reference wrapper ctor
+ * (numba_hydrodynamics_wrapper.py:9-10): width, depth, height, linear_drag_coefficient,
+ * angular_drag_coefficient, linear_damping, angular_damping, water_density, gravity,
+ * linear_mass_coeff, angular_mass_coeff, lift_coefficient; plus the body mass used by the
+ * safety clamp (hydrodynamics_behavior.py:172-173, :221-226).  Applies to every body. */
+H2O_API int h2o_set_params_uniform(h2o_handle h, const double ctor12[12], double mass);
+
+/* Part-type table (hydrodynamics_config.json "parts"): table is n_types x H2O_N_COEFF host
+ * doubles; slot_type[n_slots] maps body slot (global body index mod n_slots) to a type.
+ * The table is staged in shared memory by the kernels. */
+H2O_API int h2o_set_part_table(h2o_handle h, int n_types, const double* table_host, int n_slots,
+                               const int32_t* slot_type_host);
+
+/* Heterogeneous per-body records: coeff is (n_bodies, H2O_N_COEFF), host or device memory,
+ * src_dtype H2O_F32/H2O_F64 (converted to the handle dtype on the device). */
+H2O_API int h2o_set_params_per_body(h2o_handle h, const void* coeff, int src_dtype, h2o_stream stream);
+
+/* Articulation structure: bodies are grouped in contiguous runs of bodies_per_robot;
+ * 0 disables the per-robot wrench. */
+H2O_API int h2o_set_articulation(h2o_handle h, int bodies_per_robot);
+
+/* Isaac core hands quaternions as wxyz and the reference permutes them
+ * (hydrodynamics_behavior.py:194); the wrappers themselves take xyzw. */
+H2O_API int h2o_set_quat_order(h2o_handle h, int order);
+H2O_API int h2o_set_kernel(h2o_handle h, int choice);
+/* Accumulate global statistics inside the step kernel (device-side, no host sync). */
+H2O_API int h2o_enable_stats(h2o_handle h, int enable);
+
+/* ---- carried state ------------------------------------------------------------------
+ * _last_linear_velocity / _last_angular_velocity (hydrodynamics_behavior.py:196-198,
+ * :237-238).  h2o_reset mirrors _reset (:240-245): the next step sees zeros. */
+H2O_API int h2o_reset(h2o_handle h, h2o_stream stream);
+H2O_API int h2o_set_prev(h2o_handle h, const void* prev_lin, const void* prev_ang, h2o_stream stream);
+H2O_API int h2o_get_prev(h2o_handle h, void* prev_lin, void* prev_ang, h2o_stream stream);
+
+/* ---- fused step ---------------------------------------------------------------------
+ * Replaces HydrodynamicsBehavior._apply_behavior (hydrodynamics_behavior.py:194-238) for all
+ * bodies at once: quaternion reorder, finite-difference acceleration, every force term,
+ * body-relative lever arms, net wrench, safety clamp, previous-velocity update.
+ *   pos (N,3) quat (N,4) lin_vel (N,3) ang_vel (N,3)  ->  out_force (N,3) out_torque (N,3)
+ *   out_robot_wrench: (N / bodies_per_robot, 6) [F, tau about the robot's slot-0 body] or NULL.
+ * dt <= 1e-6 is a successful no-op (hydrodynamics_behavior.py:139). */
+H2O_API int h2o_step(h2o_handle h, const void* pos, const void* quat, const void* lin_vel,
+                     const void* ang_vel, double dt, void* out_force, void* out_torque,
+                     void* out_robot_wrench, h2o_stream stream);
+
+/* Same, PhysX tensor-API layout: transforms (N,7) = [p, q], velocities (N,6) = [v, w]
+ * (RigidPrimView.get_world_poses / get_velocities, hydrodynamics_behavior.py:178-189). */
+H2O_API int h2o_step_physx(h2o_handle h, const void* transforms, const void* velocities, double dt,
+                           void* out_force, void* out_torque, void* out_robot_wrench,
+                           h2o_stream stream);
+
+/* Bind the tensors once, then step with a single cheap call (layout: 0 split, 1 physx;
+ * for physx pass transforms as pos, velocities as lin_vel, quat = ang_vel = NULL). */
+H2O_API int h2o_bind(h2o_handle h, int layout, const void* pos, const void* quat, const void* lin_vel,
+                     const void* ang_vel, void* out_force, void* out_torque, void* out_robot_wrench);
+H2O_API int h2o_unbind(h2o_handle h);
+H2O_API int h2o_step_bound(h2o_handle h, double dt, h2o_stream stream);
+
+/* CUDA-graph rollout over the bound tensors: n_steps back-to-back steps captured once,
+ * replayed with one launch (the reference captures a single dim=1 kernel,
+ * warp_hydrodynamics_wrapper.py:101-120). */
+H2O_API int h2o_capture_rollout(h2o_handle h, int n_steps, double dt, h2o_stream stream);
+H2O_API int h2o_launch_rollout(h2o_handle h, h2o_stream stream);
+
+/* ---- full-signature components --------------------------------------------------------
+ * Replaces XHydrodynamicsWrapper.calculate_hydrodynamic_forces
+ * (numba_hydrodynamics_wrapper.py:34-53, warp_hydrodynamics_wrapper.py:79-132) =
+ * solve_hydrodynamics (numba_hydrodynamics.py:255-314), batched.  Outputs in the reference's
+ * order: buoyancy_force, drag_force, lift_force, drag_torque, added_mass_force,
+ * added_mass_torque, center_of_buoyancy, center_of_pressure (each (N,3)), sub_ratio (N,).
+ * out_flags (N, int32, may be NULL): bit0 set where the unmodified reference raises TypeError
+ * (wet body with speed <= 1e-6); the engine returns cop = cob, area = 0 there. */
+H2O_API int h2o_components(h2o_handle h, const void* pos, const void* quat, const void* lin_vel,
+                           const void* ang_vel, const void* lin_acc, const void* ang_acc,
+                           void* const out8[8], void* out_sub_ratio, int32_t* out_flags,
+                           h2o_stream stream);
+
+/* ---- host-buffer convenience path ------------------------------------------------------
+ * Numba-wrapper style call with HOST arrays (the reference's CPU flavour takes and returns
+ * NumPy arrays): chunked, double-buffered H2D -> step -> D2H on internal streams; returns
+ * after the results are in the host buffers. */
+H2O_API int h2o_step_host(h2o_handle h, const void* pos, const void* quat, const void* lin_vel,
+                          const void* ang_vel, double dt, void* out_force, void* out_torque,
+                          void* out_robot_wrench);
+
+/* ---- statistics / introspection ----------------------------------------------------------- */
+H2O_API int h2o_stats_device_ptr(h2o_handle h, void** out_ptr); /* H2O_N_STATS doubles on device */
+H2O_API int h2o_read_stats(h2o_handle h, double out[H2O_N_STATS], int reset, h2o_stream stream);
+H2O_API int64_t h2o_launch_count(h2o_handle h); /* kernels launched (or graph nodes replayed) so far */
+H2O_API int64_t h2o_n_bodies(h2o_handle h);
+H2O_API int h2o_dtype_of(h2o_handle h);
+/* Which kernel the last step used: H2O_KERNEL_TILE or H2O_KERNEL_DIRECT. */
+H2O_API int h2o_last_kernel(h2o_handle h);
+/* Device pointers of engine-owned buffers (zero-copy views for DLPack export on the host side). */
+H2O_API int h2o_prev_device_ptr(h2o_handle h, void** out_ptr);  /* (N,6) */
+H2O_API int h2o_coeff_device_ptr(h2o_handle h, void** out_ptr, int64_t* out_rows); /* (rows,11) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* H2O_H_ */

@@ -1,0 +1,679 @@
+// h2o_kernels.cuh -- sm_100a kernels of the hydrodynamics force engine.
+//
+// Replaces, for N bodies in one launch, the reference's per-body call stack
+//   HydrodynamicsBehavior._apply_behavior   hydrodynamics_behavior.py:176-238
+//   -> XHydrodynamicsWrapper.calculate_hydrodynamic_forces
+//        numba_hydrodynamics_wrapper.py:34 / warp_hydrodynamics_wrapper.py:79
+//   -> solve_hydrodynamics                  numba_hydrodynamics.py:255-314
+// (one `dim=1` Warp launch + 6 staging copies + ~30 torch micro-kernels per body).
+//
+// Two kernels share the per-body arithmetic of h2o_model.cuh:
+//
+//   step_tile_kernel   persistent CTAs; every input array of a tile of bodies is
+//                      brought into shared memory by the TMA engine
+//                      (cp.async.bulk + mbarrier, multi-stage ring), each thread
+//                      computes one body out of shared memory, results go back
+//                      through shared memory and TMA bulk stores.  Row-major
+//                      (N,3)/(N,4)/(N,6)/(N,7)/(N,11) caller layouts therefore cost
+//                      no uncoalesced or partial-sector traffic.  Optional
+//                      per-robot wrench: segmented warp-shuffle reduction.
+//   step_direct_kernel one thread per body, plain global loads; used for small
+//                      batches (latency-bound), unaligned pointers and the
+//                      full-signature `components` entry point.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "h2o_model.cuh"
+
+namespace h2o {
+
+enum : int { LAYOUT_SPLIT = 0, LAYOUT_PHYSX = 1 };
+enum : int { PARAM_TABLE = 0, PARAM_PER_BODY = 1 };
+constexpr int N_COEFF = 11;
+constexpr int MAX_TABLE_TYPES = 64;
+constexpr int MAX_TABLE_SLOTS = 256;
+constexpr int N_STATS = 8;  // sum|F|, max|F|, wet, clamped, nonfinite, still, bodies, (spare)
+
+struct StepArgs {
+    // LAYOUT_SPLIT: pos (N,3), quat (N,4), lin (N,3), ang (N,3)
+    // LAYOUT_PHYSX: pos = transforms (N,7) [p, q], lin = velocities (N,6) [v, w]
+    const void* pos;
+    const void* quat;
+    const void* lin;
+    const void* ang;
+    void* prev;              // (N,6) previous-step [v, w]; read, then overwritten
+    const void* coeff;       // PARAM_PER_BODY: (N,11); PARAM_TABLE: (n_types,11)
+    const int32_t* slot_type;  // PARAM_TABLE: (n_slots,) slot -> type
+    void* out_force;         // (N,3)
+    void* out_torque;        // (N,3)
+    void* out_wrench;        // (N / bodies_per_robot, 6) or nullptr
+    double* stats;           // N_STATS doubles or nullptr
+    long long n;             // bodies
+    long long first_body;    // global index of body 0 of this launch (slot lookup)
+    int tile_bodies;         // bodies per tile (multiple of 4 and of bodies_per_robot)
+    int n_tiles;             // number of FULL tiles handled by the TMA path
+    int n_slots, n_types;
+    int bodies_per_robot;    // 0 = no articulation
+    int quat_wxyz;           // 1: incoming quaternions are wxyz (Isaac core), else xyzw
+    double rho, grav, inv_dt;
+};
+
+// ---------------------------------------------------------------------------
+// PTX wrappers: mbarrier + bulk async copies (TMA engine, SASS UBLKCP)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// global -> shared, completion counted on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+// shared -> global, tracked by the per-thread bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
+                 "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N> __device__ __forceinline__ void bulk_wait_all()
+{
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------
+// Per-body input gather (works on shared-memory tiles and on global arrays alike)
+// ---------------------------------------------------------------------------
+template <typename S> struct BodyPtrs {
+    const S* pos;    // SPLIT: 3/body   PHYSX: 7/body
+    const S* quat;   // SPLIT: 4/body   PHYSX: unused
+    const S* lin;    // SPLIT: 3/body   PHYSX: 6/body
+    const S* ang;    // SPLIT: 3/body   PHYSX: unused
+    const S* prev;   // 6/body
+    const S* coeff;  // 11/record
+};
+
+template <typename S> struct Vec2Of;
+template <> struct Vec2Of<float> { using type = float2; };
+template <> struct Vec2Of<double> { using type = double2; };
+
+template <typename S> struct RawBody {
+    S px, py, pz, q0, q1, q2, q3;
+    S vx, vy, vz, wx, wy, wz;
+    S pvx, pvy, pvz, pwx, pwy, pwz;
+};
+
+template <typename S, int kLayout>
+__device__ __forceinline__ void load_raw(const BodyPtrs<S>& p, long long i, RawBody<S>& r)
+{
+    using V2 = typename Vec2Of<S>::type;
+    if (kLayout == LAYOUT_SPLIT) {
+        const S* pp = p.pos + 3 * i;
+        r.px = pp[0]; r.py = pp[1]; r.pz = pp[2];
+        if (sizeof(S) == 4) {
+            const float4 q = *reinterpret_cast<const float4*>(p.quat + 4 * i);
+            r.q0 = q.x; r.q1 = q.y; r.q2 = q.z; r.q3 = q.w;
+        } else {
+            const double2 qa = *reinterpret_cast<const double2*>(p.quat + 4 * i);
+            const double2 qb = *reinterpret_cast<const double2*>(p.quat + 4 * i + 2);
+            r.q0 = qa.x; r.q1 = qa.y; r.q2 = qb.x; r.q3 = qb.y;
+        }
+        const S* pv = p.lin + 3 * i;
+        r.vx = pv[0]; r.vy = pv[1]; r.vz = pv[2];
+        const S* pw = p.ang + 3 * i;
+        r.wx = pw[0]; r.wy = pw[1]; r.wz = pw[2];
+    } else {
+        const S* pp = p.pos + 7 * i;
+        r.px = pp[0]; r.py = pp[1]; r.pz = pp[2];
+        r.q0 = pp[3]; r.q1 = pp[4]; r.q2 = pp[5]; r.q3 = pp[6];
+        const V2* pv = reinterpret_cast<const V2*>(p.lin + 6 * i);
+        const V2 a = pv[0], b = pv[1], c = pv[2];
+        r.vx = a.x; r.vy = a.y; r.vz = b.x; r.wx = b.y; r.wy = c.x; r.wz = c.y;
+    }
+    const V2* pr = reinterpret_cast<const V2*>(p.prev + 6 * i);
+    const V2 a = pr[0], b = pr[1], c = pr[2];
+    r.pvx = a.x; r.pvy = a.y; r.pvz = b.x; r.pwx = b.y; r.pwy = c.x; r.pwz = c.y;
+}
+
+// Assemble the model input: quaternion order (hydrodynamics_behavior.py:194),
+// finite-difference acceleration (hydrodynamics_behavior.py:196-202), coefficients.
+template <typename S>
+__device__ __forceinline__ void make_body_in(const RawBody<S>& r, const S* c, int quat_wxyz, double rho,
+                                             double grav, S inv_dt, BodyIn<double, S>& in)
+{
+    in.pz = double(r.pz);
+    if (quat_wxyz) {
+        in.qx = double(r.q1); in.qy = double(r.q2); in.qz = double(r.q3); in.qw = double(r.q0);
+    } else {
+        in.qx = double(r.q0); in.qy = double(r.q1); in.qz = double(r.q2); in.qw = double(r.q3);
+    }
+    in.vx = r.vx; in.vy = r.vy; in.vz = r.vz;
+    in.wx = r.wx; in.wy = r.wy; in.wz = r.wz;
+    in.ax = (r.vx - r.pvx) * inv_dt; in.ay = (r.vy - r.pvy) * inv_dt; in.az = (r.vz - r.pvz) * inv_dt;
+    in.bx = (r.wx - r.pwx) * inv_dt; in.by = (r.wy - r.pwy) * inv_dt; in.bz = (r.wz - r.pwz) * inv_dt;
+    in.dimx = c[0]; in.dimy = c[1]; in.dimz = c[2];
+    in.c_drag = c[3]; in.c_drag_ang = c[4]; in.k_damp = c[5]; in.k_damp_ang = c[6];
+    in.c_am = c[7]; in.c_am_ang = c[8]; in.c_lift = c[9];
+    in.rho_h = rho; in.grav_h = grav; in.rho = S(rho);
+}
+
+// Running statistics kept in registers across a thread's bodies.
+struct ThreadStats {
+    double sum_f = 0.0, max_f = 0.0;
+    unsigned wet = 0, clamped = 0, nonfinite = 0, still = 0, bodies = 0;
+};
+
+template <typename S>
+__device__ __forceinline__ void body_step(const BodyIn<double, S>& in, S mass, S F[3], S T[3],
+                                          ThreadStats* st)
+{
+    Terms<double, S> t;
+    body_terms<double, S, false>(in, t);
+    bool clamped;
+    net_wrench<double, S>(t, mass, F, T, clamped);
+    if (st) {
+        const double mag = sqrt(double(F[0]) * double(F[0]) + double(F[1]) * double(F[1]) + double(F[2]) * double(F[2]));
+        st->bodies += 1;
+        if (mag == mag && mag < 1.7e308) {
+            st->sum_f += mag;
+            st->max_f = fmax(st->max_f, mag);
+        } else {
+            st->nonfinite += 1;
+        }
+        st->wet += (t.ratio > 0.0) ? 1u : 0u;
+        st->clamped += clamped ? 1u : 0u;
+        st->still += (t.ratio > 0.0 && t.still) ? 1u : 0u;
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ unsigned warp_sum_u(unsigned v)
+{
+    return __reduce_add_sync(0xffffffffu, v);
+}
+
+// One atomic set per warp at the very end of a (persistent) kernel.
+__device__ __forceinline__ void flush_stats(const ThreadStats& st, double* stats)
+{
+    const double s = warp_sum(st.sum_f);
+    const double m = warp_max(st.max_f);
+    const unsigned wet = warp_sum_u(st.wet), cl = warp_sum_u(st.clamped), nf = warp_sum_u(st.nonfinite),
+                   sl = warp_sum_u(st.still), nb = warp_sum_u(st.bodies);
+    if ((threadIdx.x & 31) == 0 && nb) {
+        atomicAdd(&stats[0], s);
+        // max of non-negative doubles == max of their bit patterns
+        atomicMax(reinterpret_cast<unsigned long long*>(&stats[1]),
+                  static_cast<unsigned long long>(__double_as_longlong(m)));
+        atomicAdd(&stats[2], double(wet));
+        atomicAdd(&stats[3], double(cl));
+        atomicAdd(&stats[4], double(nf));
+        atomicAdd(&stats[5], double(sl));
+        atomicAdd(&stats[6], double(nb));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Segmented warp-shuffle reduction: net wrench per robot (articulation).
+// Lanes hold consecutive bodies; `seg` is the robot index within the tile.
+// After the scan the first lane of each segment in the warp owns the partial
+// sum of that warp's slice of the robot and adds it to the tile accumulator.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void robot_reduce_warp(double v[6], int seg, bool active, double* acc /*[robots][6]*/)
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int key = active ? seg : -1 - lane;  // inactive lanes never match a neighbour
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int k2 = __shfl_down_sync(full, key, o);
+        const bool take = (lane + o < 32) && (k2 == key);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const double u = __shfl_down_sync(full, v[c], o);
+            if (take) v[c] += u;
+        }
+    }
+    const int kprev = __shfl_up_sync(full, key, 1);
+    const bool head = active && (lane == 0 || kprev != key);
+    if (head) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) atomicAdd(&acc[seg * 6 + c], v[c]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Shared-memory tile layout
+// ---------------------------------------------------------------------------
+template <typename S, int kLayout, int kParam> struct TileLayout {
+    // elements (of S) per body for each staged stream
+    static constexpr int E_POS = (kLayout == LAYOUT_SPLIT) ? 3 : 7;
+    static constexpr int E_QUAT = (kLayout == LAYOUT_SPLIT) ? 4 : 0;
+    static constexpr int E_LIN = (kLayout == LAYOUT_SPLIT) ? 3 : 6;
+    static constexpr int E_ANG = (kLayout == LAYOUT_SPLIT) ? 3 : 0;
+    static constexpr int E_PREV = 6;
+    static constexpr int E_COEFF = (kParam == PARAM_PER_BODY) ? N_COEFF : 0;
+    static constexpr int E_IN = E_POS + E_QUAT + E_LIN + E_ANG + E_PREV + E_COEFF;
+    static constexpr int E_OUT = 3 + 3 + 6;  // force, torque, prev
+};
+
+template <typename S, int kLayout, int kParam, int kThreads, int kStagesIn, int kStagesOut>
+struct TileSmem {
+    using TL = TileLayout<S, kLayout, kParam>;
+    static constexpr size_t IN_BYTES = size_t(TL::E_IN) * kThreads * sizeof(S);
+    static constexpr size_t OUT_BYTES = size_t(TL::E_OUT) * kThreads * sizeof(S);
+    static constexpr size_t TABLE_BYTES =
+        (kParam == PARAM_TABLE) ? (size_t(MAX_TABLE_TYPES) * N_COEFF * sizeof(S) + MAX_TABLE_SLOTS) : 0;
+    static constexpr size_t ROBOT_BYTES = size_t(kThreads) * 6 * sizeof(double);  // <= kThreads robots/tile
+    static constexpr size_t BAR_BYTES = 16 * sizeof(uint64_t);
+    static constexpr size_t OFF_IN = 0;
+    static constexpr size_t OFF_OUT = OFF_IN + kStagesIn * IN_BYTES;
+    static constexpr size_t OFF_TABLE = OFF_OUT + kStagesOut * OUT_BYTES;
+    static constexpr size_t OFF_ROBOT = (OFF_TABLE + TABLE_BYTES + 15) / 16 * 16;
+    static constexpr size_t total(bool robots) { return OFF_ROBOT + (robots ? ROBOT_BYTES : 0) + BAR_BYTES; }
+};
+
+// ---------------------------------------------------------------------------
+// step_tile_kernel
+// ---------------------------------------------------------------------------
+template <typename S, int kLayout, int kParam, bool kRobot, bool kStats, int kThreads, int kStagesIn,
+          int kStagesOut>
+__global__ void __launch_bounds__(kThreads) step_tile_kernel(const __grid_constant__ StepArgs a)
+{
+    using TL = TileLayout<S, kLayout, kParam>;
+    using SM = TileSmem<S, kLayout, kParam, kThreads, kStagesIn, kStagesOut>;
+    extern __shared__ __align__(128) unsigned char smem[];
+
+    const int tid = threadIdx.x;
+    const int TB = a.tile_bodies;  // bodies per tile (<= kThreads)
+    S* const table = reinterpret_cast<S*>(smem + SM::OFF_TABLE);
+    unsigned char* const slot_map = smem + SM::OFF_TABLE + size_t(MAX_TABLE_TYPES) * N_COEFF * sizeof(S);
+    double* const robot_acc = reinterpret_cast<double*>(smem + SM::OFF_ROBOT);
+    uint64_t* const full_bar =
+        reinterpret_cast<uint64_t*>(smem + SM::OFF_ROBOT + (kRobot ? SM::ROBOT_BYTES : 0));
+
+    // per-stream byte sizes of one full tile and offsets inside a stage
+    const uint32_t b_pos = uint32_t(TL::E_POS) * TB * sizeof(S);
+    const uint32_t b_quat = uint32_t(TL::E_QUAT) * TB * sizeof(S);
+    const uint32_t b_lin = uint32_t(TL::E_LIN) * TB * sizeof(S);
+    const uint32_t b_ang = uint32_t(TL::E_ANG) * TB * sizeof(S);
+    const uint32_t b_prev = uint32_t(TL::E_PREV) * TB * sizeof(S);
+    const uint32_t b_coeff = uint32_t(TL::E_COEFF) * TB * sizeof(S);
+    const uint32_t o_quat = b_pos, o_lin = o_quat + b_quat, o_ang = o_lin + b_lin, o_prev = o_ang + b_ang,
+                   o_coeff = o_prev + b_prev;
+    const uint32_t bytes_in = o_coeff + b_coeff;
+    const uint32_t b_f = 3u * TB * sizeof(S);
+    const uint32_t oo_t = b_f, oo_prev = 2 * b_f;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStagesIn; ++s) mbar_init(&full_bar[s], 1);
+        mbar_fence_init();
+        fence_proxy_async_smem();
+    }
+    if (kParam == PARAM_TABLE) {
+        const S* g = reinterpret_cast<const S*>(a.coeff);
+        for (int i = tid; i < a.n_types * N_COEFF; i += kThreads) table[i] = g[i];
+        for (int i = tid; i < a.n_slots; i += kThreads) slot_map[i] = static_cast<unsigned char>(a.slot_type[i]);
+    }
+    __syncthreads();
+
+    auto issue_loads = [&](int tile, int stage) {
+        unsigned char* dst = smem + SM::OFF_IN + size_t(stage) * SM::IN_BYTES;
+        const long long b0 = (long long)tile * TB;
+        uint64_t* bar = &full_bar[stage];
+        mbar_arrive_expect_tx(bar, bytes_in);
+        bulk_g2s(dst, reinterpret_cast<const S*>(a.pos) + b0 * TL::E_POS, b_pos, bar);
+        if (TL::E_QUAT) bulk_g2s(dst + o_quat, reinterpret_cast<const S*>(a.quat) + b0 * TL::E_QUAT, b_quat, bar);
+        bulk_g2s(dst + o_lin, reinterpret_cast<const S*>(a.lin) + b0 * TL::E_LIN, b_lin, bar);
+        if (TL::E_ANG) bulk_g2s(dst + o_ang, reinterpret_cast<const S*>(a.ang) + b0 * TL::E_ANG, b_ang, bar);
+        bulk_g2s(dst + o_prev, reinterpret_cast<const S*>(a.prev) + b0 * TL::E_PREV, b_prev, bar);
+        if (TL::E_COEFF)
+            bulk_g2s(dst + o_coeff, reinterpret_cast<const S*>(a.coeff) + b0 * TL::E_COEFF, b_coeff, bar);
+    };
+
+    const int first = blockIdx.x, stride = gridDim.x;
+    // prologue: fill kStagesIn-1 stages
+    if (tid == 0) {
+        for (int j = 0; j < kStagesIn - 1; ++j) {
+            const int tile = first + j * stride;
+            if (tile < a.n_tiles) issue_loads(tile, j);
+        }
+    }
+
+    ThreadStats st;
+    const S inv_dt = S(a.inv_dt);
+    const int bpr = a.bodies_per_robot;
+    const int robots_per_tile = kRobot ? TB / bpr : 0;
+
+    int it = 0;
+    for (int tile = first; tile < a.n_tiles; tile += stride, ++it) {
+        const int stage = it % kStagesIn;
+        const int ostage = it % kStagesOut;
+        if (tid == 0) {
+            const int nxt = tile + (kStagesIn - 1) * stride;
+            if (nxt < a.n_tiles) issue_loads(nxt, (it + kStagesIn - 1) % kStagesIn);
+        }
+        if (kRobot) {
+            for (int i = tid; i < robots_per_tile * 6; i += kThreads) robot_acc[i] = 0.0;
+        }
+        mbar_wait(&full_bar[stage], (it / kStagesIn) & 1);
+
+        const unsigned char* in = smem + SM::OFF_IN + size_t(stage) * SM::IN_BYTES;
+        BodyPtrs<S> bp;
+        bp.pos = reinterpret_cast<const S*>(in);
+        bp.quat = reinterpret_cast<const S*>(in + o_quat);
+        bp.lin = reinterpret_cast<const S*>(in + o_lin);
+        bp.ang = reinterpret_cast<const S*>(in + o_ang);
+        bp.prev = reinterpret_cast<const S*>(in + o_prev);
+        bp.coeff = reinterpret_cast<const S*>(in + o_coeff);
+
+        const bool active = tid < TB;
+        S F[3] = {S(0), S(0), S(0)}, T[3] = {S(0), S(0), S(0)};
+        RawBody<S> r;
+        if (active) {
+            load_raw<S, kLayout>(bp, tid, r);
+            const S* c;
+            if (kParam == PARAM_PER_BODY) {
+                c = bp.coeff + N_COEFF * tid;
+            } else {
+                const long long gb = a.first_body + (long long)tile * TB + tid;
+                c = table + N_COEFF * int(slot_map[int(gb % a.n_slots)]);
+            }
+            BodyIn<double, S> bin;
+            make_body_in<S>(r, c, a.quat_wxyz, a.rho, a.grav, inv_dt, bin);
+            body_step<S>(bin, c[10], F, T, kStats ? &st : nullptr);
+        }
+
+        // the bulk store that last used this output stage must have finished reading it
+        if (tid == 0) bulk_wait_read<kStagesOut - 1>();
+        __syncthreads();
+
+        unsigned char* out = smem + SM::OFF_OUT + size_t(ostage) * SM::OUT_BYTES;
+        if (active) {
+            using V2 = typename Vec2Of<S>::type;
+            S* of = reinterpret_cast<S*>(out) + 3 * tid;
+            S* ot = reinterpret_cast<S*>(out + oo_t) + 3 * tid;
+            of[0] = F[0]; of[1] = F[1]; of[2] = F[2];
+            ot[0] = T[0]; ot[1] = T[1]; ot[2] = T[2];
+            V2* op = reinterpret_cast<V2*>(reinterpret_cast<S*>(out + oo_prev) + 6 * tid);
+            V2 v;
+            v.x = r.vx; v.y = r.vy; op[0] = v;
+            v.x = r.vz; v.y = r.wx; op[1] = v;
+            v.x = r.wy; v.y = r.wz; op[2] = v;
+        }
+        if (kRobot) {
+            // wrench about the robot's slot-0 body: tau_i + (p_i - p_base) x F_i
+            double v[6] = {0, 0, 0, 0, 0, 0};
+            int seg = 0;
+            if (active) {
+                seg = tid / bpr;
+                const S* pb = bp.pos + TL::E_POS * (seg * bpr);
+                const double ax = double(r.px) - double(pb[0]), ay = double(r.py) - double(pb[1]),
+                             az = double(r.pz) - double(pb[2]);
+                const double fx = double(F[0]), fy = double(F[1]), fz = double(F[2]);
+                v[0] = fx; v[1] = fy; v[2] = fz;
+                v[3] = double(T[0]) + (ay * fz - az * fy);
+                v[4] = double(T[1]) + (az * fx - ax * fz);
+                v[5] = double(T[2]) + (ax * fy - ay * fx);
+            }
+            robot_reduce_warp(v, seg, active, robot_acc);
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+
+        if (tid == 0) {
+            const long long b0 = (long long)tile * TB;
+            bulk_s2g(reinterpret_cast<S*>(a.out_force) + b0 * 3, out, b_f);
+            bulk_s2g(reinterpret_cast<S*>(a.out_torque) + b0 * 3, out + oo_t, b_f);
+            bulk_s2g(reinterpret_cast<S*>(a.prev) + b0 * 6, out + oo_prev, b_prev);
+            bulk_commit();
+        }
+        if (kRobot) {
+            S* ow = reinterpret_cast<S*>(a.out_wrench) + ((long long)tile * robots_per_tile) * 6;
+            for (int i = tid; i < robots_per_tile * 6; i += kThreads) ow[i] = S(robot_acc[i]);
+            __syncthreads();  // robot_acc is re-zeroed at the top of the next iteration
+        }
+    }
+    if (tid == 0) bulk_wait_all<0>();
+    if (kStats && a.stats) flush_stats(st, a.stats);
+}
+
+// ---------------------------------------------------------------------------
+// step_direct_kernel: one thread per body, plain global loads/stores.
+// Processes bodies [body_begin, n).  Robot wrench (if requested) is produced by
+// robot_wrench_kernel below from the written force/torque arrays.
+// ---------------------------------------------------------------------------
+template <typename S, int kLayout, int kParam, bool kStats>
+__global__ void __launch_bounds__(256) step_direct_kernel(const __grid_constant__ StepArgs a, long long body_begin)
+{
+    __shared__ S table[(kParam == PARAM_TABLE) ? MAX_TABLE_TYPES * N_COEFF : 1];
+    __shared__ unsigned char slot_map[(kParam == PARAM_TABLE) ? MAX_TABLE_SLOTS : 1];
+    if (kParam == PARAM_TABLE) {
+        const S* g = reinterpret_cast<const S*>(a.coeff);
+        for (int i = threadIdx.x; i < a.n_types * N_COEFF; i += blockDim.x) table[i] = g[i];
+        for (int i = threadIdx.x; i < a.n_slots; i += blockDim.x)
+            slot_map[i] = static_cast<unsigned char>(a.slot_type[i]);
+        __syncthreads();
+    }
+    ThreadStats st;
+    const long long i = body_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n) {
+        BodyPtrs<S> bp;
+        bp.pos = reinterpret_cast<const S*>(a.pos);
+        bp.quat = reinterpret_cast<const S*>(a.quat);
+        bp.lin = reinterpret_cast<const S*>(a.lin);
+        bp.ang = reinterpret_cast<const S*>(a.ang);
+        bp.prev = reinterpret_cast<const S*>(a.prev);
+        bp.coeff = reinterpret_cast<const S*>(a.coeff);
+        RawBody<S> r;
+        load_raw<S, kLayout>(bp, i, r);
+        S cl[N_COEFF];
+        if (kParam == PARAM_PER_BODY) {
+#pragma unroll
+            for (int k = 0; k < N_COEFF; ++k) cl[k] = __ldg(bp.coeff + N_COEFF * i + k);
+        } else {
+            const S* c = table + N_COEFF * int(slot_map[int((a.first_body + i) % a.n_slots)]);
+#pragma unroll
+            for (int k = 0; k < N_COEFF; ++k) cl[k] = c[k];
+        }
+        BodyIn<double, S> bin;
+        make_body_in<S>(r, cl, a.quat_wxyz, a.rho, a.grav, S(a.inv_dt), bin);
+        S F[3], T[3];
+        body_step<S>(bin, cl[10], F, T, kStats ? &st : nullptr);
+        S* of = reinterpret_cast<S*>(a.out_force) + 3 * i;
+        S* ot = reinterpret_cast<S*>(a.out_torque) + 3 * i;
+        of[0] = F[0]; of[1] = F[1]; of[2] = F[2];
+        ot[0] = T[0]; ot[1] = T[1]; ot[2] = T[2];
+        using V2 = typename Vec2Of<S>::type;
+        V2* op = reinterpret_cast<V2*>(reinterpret_cast<S*>(a.prev) + 6 * i);
+        V2 v;
+        v.x = r.vx; v.y = r.vy; op[0] = v;
+        v.x = r.vz; v.y = r.wx; op[1] = v;
+        v.x = r.wy; v.y = r.wz; op[2] = v;
+    }
+    if (kStats && a.stats) flush_stats(st, a.stats);
+}
+
+// Robot wrench from written force/torque arrays for robots [robot_begin, n_robots):
+// one warp per robot, lanes stride over its bodies, shuffle reduction.
+template <typename S, int kLayout>
+__global__ void __launch_bounds__(256) robot_wrench_kernel(const __grid_constant__ StepArgs a, long long robot_begin)
+{
+    const long long robot = robot_begin + ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+    const int lane = threadIdx.x & 31;
+    const long long n_robots = a.n / a.bodies_per_robot;
+    if (robot >= n_robots) return;
+    constexpr int EP = (kLayout == LAYOUT_SPLIT) ? 3 : 7;
+    const S* pos = reinterpret_cast<const S*>(a.pos);
+    const S* Fp = reinterpret_cast<const S*>(a.out_force);
+    const S* Tp = reinterpret_cast<const S*>(a.out_torque);
+    const long long b0 = robot * a.bodies_per_robot;
+    const double bx = double(pos[EP * b0]), by = double(pos[EP * b0 + 1]), bz = double(pos[EP * b0 + 2]);
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    for (int j = lane; j < a.bodies_per_robot; j += 32) {
+        const long long i = b0 + j;
+        const double fx = double(Fp[3 * i]), fy = double(Fp[3 * i + 1]), fz = double(Fp[3 * i + 2]);
+        const double ax = double(pos[EP * i]) - bx, ay = double(pos[EP * i + 1]) - by,
+                     az = double(pos[EP * i + 2]) - bz;
+        v[0] += fx; v[1] += fy; v[2] += fz;
+        v[3] += double(Tp[3 * i]) + (ay * fz - az * fy);
+        v[4] += double(Tp[3 * i + 1]) + (az * fx - ax * fz);
+        v[5] += double(Tp[3 * i + 2]) + (ax * fy - ay * fx);
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) v[c] = warp_sum(v[c]);
+    if (lane == 0) {
+        S* ow = reinterpret_cast<S*>(a.out_wrench) + robot * 6;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) ow[c] = S(v[c]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// components_kernel: batched solve_hydrodynamics (numba_hydrodynamics.py:255-314),
+// reference output order: buoyancy_force, drag_force, lift_force, drag_torque,
+// added_mass_force, added_mass_torque, center_of_buoyancy, center_of_pressure, sub_ratio.
+// cob/cop are returned in world coordinates like the reference (zeros when dry).
+// ---------------------------------------------------------------------------
+struct ComponentsArgs {
+    const void *pos, *quat, *lin, *ang, *lin_acc, *ang_acc;
+    const void* coeff;
+    const int32_t* slot_type;
+    void* out[8];     // eight (N,3) arrays
+    void* out_ratio;  // (N,)
+    int32_t* out_flags;  // (N,) bit0 = "reference raises" (wet, speed <= 1e-6), may be null
+    long long n, first_body;
+    int n_slots, n_types, param_mode, quat_wxyz;
+    double rho, grav;
+};
+
+template <typename S>
+__global__ void __launch_bounds__(256) components_kernel(const __grid_constant__ ComponentsArgs a)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const S* c;
+    if (a.param_mode == PARAM_PER_BODY) c = reinterpret_cast<const S*>(a.coeff) + N_COEFF * i;
+    else c = reinterpret_cast<const S*>(a.coeff) + N_COEFF * a.slot_type[(a.first_body + i) % a.n_slots];
+    RawBody<S> r;
+    const S* p = reinterpret_cast<const S*>(a.pos) + 3 * i;
+    const S* q = reinterpret_cast<const S*>(a.quat) + 4 * i;
+    const S* v = reinterpret_cast<const S*>(a.lin) + 3 * i;
+    const S* w = reinterpret_cast<const S*>(a.ang) + 3 * i;
+    const S* la = reinterpret_cast<const S*>(a.lin_acc) + 3 * i;
+    const S* aa = reinterpret_cast<const S*>(a.ang_acc) + 3 * i;
+    r.px = p[0]; r.py = p[1]; r.pz = p[2];
+    r.q0 = q[0]; r.q1 = q[1]; r.q2 = q[2]; r.q3 = q[3];
+    r.vx = v[0]; r.vy = v[1]; r.vz = v[2];
+    r.wx = w[0]; r.wy = w[1]; r.wz = w[2];
+    r.pvx = r.vx; r.pvy = r.vy; r.pvz = r.vz; r.pwx = r.wx; r.pwy = r.wy; r.pwz = r.wz;
+    BodyIn<double, S> in;
+    make_body_in<S>(r, c, a.quat_wxyz, a.rho, a.grav, S(0), in);
+    in.ax = la[0]; in.ay = la[1]; in.az = la[2];
+    in.bx = aa[0]; in.by = aa[1]; in.bz = aa[2];
+    Terms<double, S> t;
+    body_terms<double, S, false>(in, t);
+    const bool wet = t.ratio > 0.0;
+    S* o;
+    o = reinterpret_cast<S*>(a.out[0]) + 3 * i; o[0] = S(0); o[1] = S(0); o[2] = S(t.fbz);
+    o = reinterpret_cast<S*>(a.out[1]) + 3 * i; o[0] = t.fd[0]; o[1] = t.fd[1]; o[2] = t.fd[2];
+    o = reinterpret_cast<S*>(a.out[2]) + 3 * i; o[0] = t.fl[0]; o[1] = t.fl[1]; o[2] = t.fl[2];
+    o = reinterpret_cast<S*>(a.out[3]) + 3 * i; o[0] = t.td[0]; o[1] = t.td[1]; o[2] = t.td[2];
+    o = reinterpret_cast<S*>(a.out[4]) + 3 * i; o[0] = t.fam[0]; o[1] = t.fam[1]; o[2] = t.fam[2];
+    o = reinterpret_cast<S*>(a.out[5]) + 3 * i; o[0] = t.tam[0]; o[1] = t.tam[1]; o[2] = t.tam[2];
+    o = reinterpret_cast<S*>(a.out[6]) + 3 * i;
+    o[0] = wet ? S(double(r.px) + double(t.cob[0])) : S(0);
+    o[1] = wet ? S(double(r.py) + double(t.cob[1])) : S(0);
+    o[2] = wet ? S(double(r.pz) + double(t.cob[2])) : S(0);
+    o = reinterpret_cast<S*>(a.out[7]) + 3 * i;
+    o[0] = wet ? S(double(r.px) + double(t.cop[0])) : S(0);
+    o[1] = wet ? S(double(r.py) + double(t.cop[1])) : S(0);
+    o[2] = wet ? S(double(r.pz) + double(t.cop[2])) : S(0);
+    reinterpret_cast<S*>(a.out_ratio)[i] = S(t.ratio);
+    if (a.out_flags) a.out_flags[i] = (wet && t.still) ? 1 : 0;
+}
+
+// dtype conversion / packing helpers -----------------------------------------
+template <typename D, typename Sx>
+__global__ void cast_kernel(D* dst, const Sx* src, long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = D(src[i]);
+}
+// (N,3)+(N,3) <-> (N,6)
+template <typename S> __global__ void pack_prev_kernel(S* prev, const S* lin, const S* ang, long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        for (int k = 0; k < 3; ++k) {
+            prev[6 * i + k] = lin[3 * i + k];
+            prev[6 * i + 3 + k] = ang[3 * i + k];
+        }
+    }
+}
+template <typename S> __global__ void unpack_prev_kernel(const S* prev, S* lin, S* ang, long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        for (int k = 0; k < 3; ++k) {
+            lin[3 * i + k] = prev[6 * i + k];
+            ang[3 * i + k] = prev[6 * i + 3 + k];
+        }
+    }
+}
+
+}  // namespace h2o

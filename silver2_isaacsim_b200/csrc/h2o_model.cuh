@@ -1,0 +1,444 @@
+// h2o_model.cuh -- per-body hydrodynamic force model, structured for a box.
+//
+// WHAT is computed follows the reference (citations relative to
+// /root/reference/src/scripts/physics/):
+//   numba_hydrodynamics.py:8-51    quaternion_to_matrix (xyzw, no normalisation)
+//   numba_hydrodynamics.py:53-105  analyze_submersion_and_cob
+//   numba_hydrodynamics.py:107-143 calculate_pressure_and_area
+//   numba_hydrodynamics.py:145-182 calculate_hybrid_drag
+//   numba_hydrodynamics.py:184-217 calculate_lift
+//   numba_hydrodynamics.py:219-253 calculate_added_mass
+//   numba_hydrodynamics.py:255-314 solve_hydrodynamics
+//   numba_hydrodynamics_wrapper.py:55-112 box keypoints / faces / added-mass diagonal
+//   hydrodynamics_behavior.py:194-238 finite-difference accel, lever arms, clamp
+//
+// HOW is different: nothing is looped over 27 keypoints / 6 faces / a 6x6 matrix.
+// The box structure is used instead:
+//   * a keypoint's world height is  p_z + (i*a + j*b) + k*c  with i,j,k in {-1,0,1},
+//     a = R20*hx, b = R21*hy, c = R22*hz  -> 13 sums up to sign, 27 compares that
+//     build a 27-bit "submerged" mask; centre of buoyancy comes from popcounts.
+//   * the six face centres ARE six of those keypoints, so their wet tests are mask bits;
+//     face normals are +-columns of R, so only one face per axis can oppose the flow.
+//   * lever arms (cob - p, cop - p) are evaluated body-relative: the x,y translation
+//     never enters and the reference's world-space cancellation is avoided.
+//   * the added-mass matrix is diagonal.
+//
+// Precision policy: H ("high") carries the waterline (row 2 of R, the 27 tests,
+// z_min/z_max, submersion ratio, buoyancy) and the final force/torque sums;
+// L ("low") carries everything else.  fp64 mode: H = L = double.  fp32 mode:
+// H = double, L = float (storage and traffic stay fp32).
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define H2O_HD __host__ __device__ __forceinline__
+#else
+#define H2O_HD inline
+#endif
+
+namespace h2o {
+
+// ---- small math helpers ---------------------------------------------------
+// fp32: MUFU approximation + one Newton step (full fp32 accuracy for normal, positive
+// arguments; no IEEE special-case slow path -> no divergent subroutine calls).
+// fp64: plain IEEE operations (fp64 mode has twice the time budget per body).
+H2O_HD float h2o_abs(float x) { return fabsf(x); }
+H2O_HD double h2o_abs(double x) { return fabs(x); }
+H2O_HD float h2o_min(float a, float b) { return fminf(a, b); }
+H2O_HD double h2o_min(double a, double b) { return fmin(a, b); }
+H2O_HD float h2o_max(float a, float b) { return fmaxf(a, b); }
+H2O_HD double h2o_max(double a, double b) { return fmax(a, b); }
+
+// 1/x, x > 0
+H2O_HD float h2o_rcp(float x)
+{
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+#else
+    return 1.0f / x;
+#endif
+}
+H2O_HD double h2o_rcp(double x) { return 1.0 / x; }
+
+// 1/sqrt(x), x > 0
+H2O_HD float h2o_rsqrt(float x)
+{
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    const float t = x * y;
+    return fmaf(0.5f * y, fmaf(-t, y, 1.0f), y);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+H2O_HD double h2o_rsqrt(double x) { return 1.0 / sqrt(x); }
+
+// sqrt(x) given r = h2o_rsqrt(x):  x*r, with one correction step in fp32
+H2O_HD float h2o_sqrt_from_rsqrt(float x, float r)
+{
+    const float s = x * r;
+    return fmaf(fmaf(-s, s, x), 0.5f * r, s);
+}
+H2O_HD double h2o_sqrt_from_rsqrt(double x, double) { return sqrt(x); }
+
+// 1/x for the waterline ratio (H precision).  Device: approximation + two Newton steps.
+H2O_HD double h2o_rcp_h(double x)
+{
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+#else
+    return 1.0 / x;
+#endif
+}
+
+H2O_HD float h2o_rcp_h(float x) { return 1.0f / x; }
+
+H2O_HD int h2o_popc(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+
+// mask |= bit  if  t < m      (one compare + one predicated OR on the device)
+H2O_HD void h2o_or_if_less(uint32_t& mask, double t, double m, uint32_t bit)
+{
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}"
+        : "+r"(mask)
+        : "d"(t), "d"(m), "r"(bit));
+#else
+    if (t < m) mask |= bit;
+#endif
+}
+H2O_HD void h2o_or_if_less(uint32_t& mask, float t, float m, uint32_t bit)
+{
+    if (t < m) mask |= bit;
+}
+
+// Lift coefficient sin(2*asin(d)) (numba_hydrodynamics.py:197-203), d already clipped.
+// kExactTrig follows the reference literally.  Otherwise the identity
+// sin(2 asin d) = 2 d sqrt(1 - d^2) is used with 1 - d^2 supplied by the caller from
+// a well-conditioned expression (|v_hat x up|^2 - (|up|^2 - 1)), because forming
+// 1 - d*d from a rounded d loses all accuracy as |d| -> 1.
+template <bool kExactTrig> H2O_HD double lift_coefficient_of(double d, double one_minus_d2)
+{
+    if (kExactTrig) return sin(2.0 * asin(d));
+    return 2.0 * d * sqrt(fmax(0.0, one_minus_d2));
+}
+template <bool kExactTrig> H2O_HD float lift_coefficient_of(float d, float one_minus_d2)
+{
+    if (kExactTrig) return sinf(2.0f * asinf(d));
+    const float x = fmaxf(one_minus_d2, 1e-30f);
+    return 2.0f * d * h2o_sqrt_from_rsqrt(x, h2o_rsqrt(x));
+}
+
+// ---- keypoint bit layout --------------------------------------------------
+// bit(i,j,k) = (i+1) + 3*(j+1) + 9*(k+1), i/j/k = sign of the x/y/z offset.
+constexpr int kp_bit(int i, int j, int k) { return (i + 1) + 3 * (j + 1) + 9 * (k + 1); }
+constexpr uint32_t kp_mask_axis(int axis, int sign)
+{
+    uint32_t m = 0;
+    for (int i = -1; i <= 1; ++i)
+        for (int j = -1; j <= 1; ++j)
+            for (int k = -1; k <= 1; ++k) {
+                const int s = axis == 0 ? i : (axis == 1 ? j : k);
+                if (s == sign) m |= 1u << kp_bit(i, j, k);
+            }
+    return m;
+}
+constexpr uint32_t KP_ALL = (1u << 27) - 1u;
+constexpr uint32_t KP_XP = kp_mask_axis(0, +1), KP_XN = kp_mask_axis(0, -1);
+constexpr uint32_t KP_YP = kp_mask_axis(1, +1), KP_YN = kp_mask_axis(1, -1);
+constexpr uint32_t KP_ZP = kp_mask_axis(2, +1), KP_ZN = kp_mask_axis(2, -1);
+
+// ---- inputs / outputs -----------------------------------------------------
+template <typename H, typename L> struct BodyIn {
+    H pz;                 // height of the body origin above the z = 0 waterline
+    H qx, qy, qz, qw;     // orientation, xyzw
+    L vx, vy, vz;         // linear velocity (world)
+    L wx, wy, wz;         // angular velocity (world)
+    L ax, ay, az;         // linear acceleration (world)
+    L bx, by, bz;         // angular acceleration (world)
+    // coefficient record (params.py COEFF_FIELDS) + globals
+    L dimx, dimy, dimz;
+    L c_drag, c_drag_ang, k_damp, k_damp_ang, c_am, c_am_ang, c_lift;
+    H rho_h, grav_h;      // globals: waterDensity, gravity (H for buoyancy)
+    L rho;                // = L(rho_h)
+};
+
+template <typename H, typename L> struct Terms {
+    H ratio;              // submersion ratio (0 => every other field is 0)
+    H fbz;                // buoyancy force, +z (numba_hydrodynamics.py:282)
+    L fd[3];              // drag force
+    L fl[3];              // lift force
+    L td[3];              // drag torque
+    L fam[3];             // added-mass force
+    L tam[3];             // added-mass torque
+    L cob[3];             // centre of buoyancy - p   (body-relative lever arm, world axes)
+    L cop[3];             // centre of pressure - p
+    L tarm[3];            // (cop - p) x drag force, evaluated without cancellation
+    uint32_t kp_mask;     // 27-bit submerged-keypoint mask (diagnostic)
+    bool still;           // wet and speed <= 1e-6: the reference raises here
+};
+
+// One body, branch-free.  kExactTrig: asin/sin as the reference vs 2d*sqrt(1-d^2).
+template <typename H, typename L, bool kExactTrig>
+H2O_HD void body_terms(const BodyIn<H, L>& in, Terms<H, L>& t)
+{
+    // ---- rotation (numba_hydrodynamics.py:14-49).  Row 2 in H for the waterline.
+    const H hx2 = in.qx + in.qx, hy2 = in.qy + in.qy, hz2 = in.qz + in.qz;
+    const H r20h = in.qx * hz2 - in.qw * hy2;
+    const H r21h = in.qy * hz2 + in.qw * hx2;
+    const H r22h = H(1) - (in.qx * hx2 + in.qy * hy2);
+    // |q|^2 - 1: the reference never normalises, so R is orthogonal only up to this.
+    const H dqh = ((in.qx * in.qx + in.qy * in.qy) + (in.qz * in.qz + in.qw * in.qw)) - H(1);
+
+    // ---- waterline: 27 keypoints {-hx,0,hx}x{hy,0,-hy}x{hz,0,-hz}
+    //      (numba_hydrodynamics_wrapper.py:55-73, numba_hydrodynamics.py:271, :59-105)
+    const H dxh = H(in.dimx), dyh = H(in.dimy), dzh = H(in.dimz);
+    const H a = r20h * (dxh * H(0.5));
+    const H b = r21h * (dyh * H(0.5));
+    const H c = r22h * (dzh * H(0.5));
+    const H abp = a + b, abm = a - b;
+    const H m = -in.pz;  // keypoint wet  <=>  fl(t + pz) < 0  <=>  t < -pz  (exact)
+    uint32_t mask = 0;
+#define H2O_KP(i, j, k, tval)                                                   \
+    {                                                                           \
+        const H tv = (tval);                                                    \
+        h2o_or_if_less(mask, tv, m, 1u << kp_bit(i, j, k));                     \
+        h2o_or_if_less(mask, -tv, m, 1u << kp_bit(-(i), -(j), -(k)));           \
+    }
+    H2O_KP(1, 0, 0, a)
+    H2O_KP(0, 1, 0, b)
+    H2O_KP(1, 1, 0, abp)
+    H2O_KP(1, -1, 0, abm)
+    H2O_KP(0, 0, 1, c)
+    H2O_KP(1, 0, 1, a + c)
+    H2O_KP(1, 0, -1, a - c)
+    H2O_KP(0, 1, 1, b + c)
+    H2O_KP(0, 1, -1, b - c)
+    H2O_KP(1, 1, 1, abp + c)
+    H2O_KP(1, 1, -1, abp - c)
+    H2O_KP(1, -1, 1, abm + c)
+    H2O_KP(1, -1, -1, abm - c)
+#undef H2O_KP
+    h2o_or_if_less(mask, H(0), m, 1u << kp_bit(0, 0, 0));
+
+    const H ext = (h2o_abs(a) + h2o_abs(b)) + h2o_abs(c);  // highest keypoint above p
+    const H z_min = in.pz - ext, z_max = in.pz + ext;
+    const bool dry = z_min >= H(0);
+    const bool partial = !dry && !(z_max <= H(0));
+    const H total_height = z_max - z_min;
+    H ratio = H(1);
+    if (partial && !(total_height < H(1e-6))) ratio = h2o_min(H(1), -z_min * h2o_rcp_h(total_height));
+    if (dry || !(ratio > H(1e-9))) ratio = H(0);  // numba_hydrodynamics.py:87, :277-279
+
+    t.kp_mask = mask;
+    t.ratio = ratio;
+    const L rl = L(ratio);  // 0 for a dry body: every force below is scaled by it
+
+    // ---- full rotation matrix in L
+    const L qx = L(in.qx), qy = L(in.qy), qz = L(in.qz), qw = L(in.qw);
+    const L x2 = qx + qx, y2 = qy + qy, z2 = qz + qz;
+    const L xx = qx * x2, xy = qx * y2, xz = qx * z2;
+    const L yy = qy * y2, yz = qy * z2, zz = qz * z2;
+    const L wx = qw * x2, wy = qw * y2, wz = qw * z2;
+    const L r00 = L(1) - (yy + zz), r01 = xy - wz, r02 = xz + wy;
+    const L r10 = xy + wz, r11 = L(1) - (xx + zz), r12 = yz - wx;
+    const L r20 = L(r20h), r21 = L(r21h), r22 = L(r22h);
+    const L dq = L(dqh);
+
+    const L hx = in.dimx * L(0.5), hy = in.dimy * L(0.5), hz = in.dimz * L(0.5);
+    const L ayz = in.dimy * in.dimz, axz = in.dimx * in.dimz, axy = in.dimx * in.dimy;  // face areas
+    const L vol = in.dimx * ayz;  // numba_hydrodynamics_wrapper.py:15
+
+    // ---- buoyancy (numba_hydrodynamics.py:282)
+    t.fbz = in.rho_h * (ratio * (dxh * dyh * dzh)) * in.grav_h;
+
+    // ---- centre of buoyancy, body-relative: R * (h .* sum(sign)/count)
+    const int cnt = h2o_popc(mask);
+    const L cinv = (partial && cnt > 0) ? h2o_rcp(L(cnt)) : L(0);
+    const L csx = L(h2o_popc(mask & KP_XP) - h2o_popc(mask & KP_XN)) * (cinv * hx);
+    const L csy = L(h2o_popc(mask & KP_YP) - h2o_popc(mask & KP_YN)) * (cinv * hy);
+    const L csz = L(h2o_popc(mask & KP_ZP) - h2o_popc(mask & KP_ZN)) * (cinv * hz);
+    const L cobx = r00 * csx + r01 * csy + r02 * csz;
+    const L coby = r10 * csx + r11 * csy + r12 * csz;
+    const L cobz = r20 * csx + r21 * csy + r22 * csz;
+
+    // ---- flow direction (numba_hydrodynamics.py:285-289)
+    const L speed2 = in.vx * in.vx + in.vy * in.vy + in.vz * in.vz;
+    const L rs = h2o_rsqrt(h2o_max(speed2, L(1e-30)));
+    const L speed = h2o_sqrt_from_rsqrt(speed2, rs);
+    const bool moving = speed > L(1e-6);
+    const L inv_speed = moving ? rs : L(0);
+    const L ux = in.vx * inv_speed, uy = in.vy * inv_speed, uz = in.vz * inv_speed;
+    t.still = !moving && (ratio > H(0));
+
+    // ---- projected area + centre of pressure (numba_hydrodynamics.py:113-143).
+    // Face normals are +-columns of R; the face opposing the flow on axis j is the one with
+    // sign -sgn(d_j), alignment |d_j|, centre = that sign * h_j * R[:,j].  Its wet test is the
+    // keypoint bit of the face centre (strict <, in every regime).
+    const L d0 = r00 * ux + r10 * uy + r20 * uz;
+    const L d1 = r01 * ux + r11 * uy + r21 * uz;
+    const L d2 = r02 * ux + r12 * uy + r22 * uz;
+    const uint32_t f0 = (d0 < L(0)) ? (1u << kp_bit(1, 0, 0)) : (1u << kp_bit(-1, 0, 0));
+    const uint32_t f1 = (d1 < L(0)) ? (1u << kp_bit(0, 1, 0)) : (1u << kp_bit(0, -1, 0));
+    const uint32_t f2 = (d2 < L(0)) ? (1u << kp_bit(0, 0, 1)) : (1u << kp_bit(0, 0, -1));
+    const L w0 = (mask & f0) ? L(1) : L(0), w1 = (mask & f1) ? L(1) : L(0), w2 = (mask & f2) ? L(1) : L(0);
+    // s_j * area = -h_j A_j w_j d_j ;  alignment*area = |d_j| A_j w_j
+    const L g0 = w0 * d0, g1 = w1 * d1, g2 = w2 * d2;
+    const L area = (h2o_abs(g0) * ayz + h2o_abs(g1) * axz) + h2o_abs(g2) * axy;
+    const bool faces = area > L(1e-6);
+    const L inv_area = faces ? h2o_rcp(area) : L(0);
+    const L ginv = (vol * L(0.5)) * inv_area;  // h_j A_j / area, identical on the three axes
+    const L s0 = -(ginv * g0), s1 = -(ginv * g1), s2 = -(ginv * g2);
+    const L copx = faces ? (r00 * s0 + r01 * s1 + r02 * s2) : cobx;
+    const L copy = faces ? (r10 * s0 + r11 * s1 + r12 * s2) : coby;
+    const L copz = faces ? (r20 * s0 + r21 * s1 + r22 * s2) : cobz;
+
+    // ---- hybrid drag (numba_hydrodynamics.py:153-182)
+    const L low = L(0.2);
+    const L quad = L(0.5) * in.rho * speed2 * in.c_drag * area;  // area = 0 unless moving
+    const L kd = in.k_damp * h2o_min(L(1), speed * L(5.0));
+    t.fd[0] = (-(quad * ux) - kd * in.vx) * rl;
+    t.fd[1] = (-(quad * uy) - kd * in.vy) * rl;
+    t.fd[2] = (-(quad * uz) - kd * in.vz) * rl;
+
+    // Lever-arm torque of the drag force, (cop - p) x F_d (hydrodynamics_behavior.py:213).
+    // F_d = -psi * v_hat is anti-parallel to the flow and, because h_j * A_j = V/2 on
+    // every axis, the face-weighted arm is  cop - p = R s,  s_j = -(V/2A) w_j d_j  with
+    // d = R^T v_hat and w_j = [opposing face of axis j is wet].  When every opposing face
+    // is wet s is parallel to d and the reference's world-space cross product is pure
+    // cancellation (what survives is an artefact of the un-normalised quaternion,
+    // R R^T = I - 4 dq [u]x^2, u = vector part, dq = |q|^2 - 1).  Evaluated in the body
+    // frame, to first order in dq, nothing cancels:
+    //   v_hat x (R s) = R c + 4 dq ( u (u . R c) + (u (u.v_hat) - |u|^2 v_hat) x (R s) ),
+    //   c = d x s,  c_x = -(V/2A) d_y d_z (w_z - w_y)  (cyclic).
+    // Without face contributions (cop = cob) the plain cross product is used.
+    {
+        const L psi = faces ? (quad + kd * speed) * rl : L(0);
+        const L c0 = -(ginv * d1 * d2 * (w2 - w1));
+        const L c1 = -(ginv * d2 * d0 * (w0 - w2));
+        const L c2 = -(ginv * d0 * d1 * (w1 - w0));
+        const L rcx = r00 * c0 + r01 * c1 + r02 * c2;
+        const L rcy = r10 * c0 + r11 * c1 + r12 * c2;
+        const L rcz = r20 * c0 + r21 * c1 + r22 * c2;
+        const L k4 = L(4) * dq;
+        const L udu = qx * ux + qy * uy + qz * uz;
+        const L uu = qx * qx + qy * qy + qz * qz;
+        const L gx = qx * udu - uu * ux, gy = qy * udu - uu * uy, gz = qz * udu - uu * uz;
+        const L urc = qx * rcx + qy * rcy + qz * rcz;
+        // plain arm x F_d, kept only when the arm is the centre of buoyancy
+        const L nf = faces ? L(0) : L(1);
+        const L px = (coby * t.fd[2] - cobz * t.fd[1]) * nf;
+        const L py = (cobz * t.fd[0] - cobx * t.fd[2]) * nf;
+        const L pz = (cobx * t.fd[1] - coby * t.fd[0]) * nf;
+        t.tarm[0] = psi * (rcx + k4 * (qx * urc + (gy * copz - gz * copy))) + px;
+        t.tarm[1] = psi * (rcy + k4 * (qy * urc + (gz * copx - gx * copz))) + py;
+        t.tarm[2] = psi * (rcz + k4 * (qz * urc + (gx * copy - gy * copx))) + pz;
+    }
+    {
+        const L as2 = in.wx * in.wx + in.wy * in.wy + in.wz * in.wz;
+        const L as = h2o_sqrt_from_rsqrt(as2, h2o_rsqrt(h2o_max(as2, L(1e-30))));
+        // -(0.5 rho |w|^2 C V) * w/|w|  ==  -(0.5 rho |w| C V) * w
+        const L aq = (as > L(1e-6)) ? L(0.5) * in.rho * as * in.c_drag_ang * vol : L(0);
+        const L ka = (aq + in.k_damp_ang * h2o_min(L(1), as * L(5.0))) * rl;
+        t.td[0] = -(ka * in.wx);
+        t.td[1] = -(ka * in.wy);
+        t.td[2] = -(ka * in.wz);
+    }
+    (void)low;
+
+    // ---- lift (numba_hydrodynamics.py:191-217); up = R[:,2], so -up.v_hat = -d2
+    {
+        // axis = v_hat x up ; dir = (axis/|axis|) x v_hat
+        const L axx = uy * r22 - uz * r12;
+        const L axy_ = uz * r02 - ux * r22;
+        const L axz_ = ux * r12 - uy * r02;
+        const L an2 = axx * axx + axy_ * axy_ + axz_ * axz_;
+        const L ra = h2o_rsqrt(h2o_max(an2, L(1e-30)));
+        const L an = h2o_sqrt_from_rsqrt(an2, ra);
+        const bool ok = !(speed < L(1e-6)) && !(an < L(1e-6));
+        const L dd = h2o_max(L(-1), h2o_min(L(1), -d2));
+        // 1 - d^2 = |v_hat x up|^2 - (|up|^2 - 1),  |up|^2 - 1 = 4 dq (qx^2 + qy^2)
+        const L eta = L(4) * dq * (qx * qx + qy * qy);
+        const L cl = lift_coefficient_of<kExactTrig>(dd, an2 - eta);
+        const L mag = L(0.5) * in.rho * speed2 * cl * area * in.c_lift;
+        const L s = ok ? mag * rl * ra : L(0);
+        t.fl[0] = (axy_ * uz - axz_ * uy) * s;
+        t.fl[1] = (axz_ * ux - axx * uz) * s;
+        t.fl[2] = (axx * uy - axy_ * ux) * s;
+    }
+
+    // ---- added mass (numba_hydrodynamics.py:224-253; diagonal of
+    //      numba_hydrodynamics_wrapper.py:101-112): -R diag(M) R^T acc * ratio
+    {
+        const L ml = vol * in.c_am * in.rho * rl;
+        const L lx = r00 * in.ax + r10 * in.ay + r20 * in.az;
+        const L ly = r01 * in.ax + r11 * in.ay + r21 * in.az;
+        const L lz = r02 * in.ax + r12 * in.ay + r22 * in.az;
+        const L fx = -(ml * lx), fy = -(ml * ly), fz = -(ml * lz);
+        t.fam[0] = r00 * fx + r01 * fy + r02 * fz;
+        t.fam[1] = r10 * fx + r11 * fy + r12 * fz;
+        t.fam[2] = r20 * fx + r21 * fy + r22 * fz;
+
+        const L ma = vol * in.c_am_ang * in.rho * rl;
+        const L w2s = in.dimx * in.dimx, d2s = in.dimy * in.dimy, h2s = in.dimz * in.dimz;
+        const L gx = r00 * in.bx + r10 * in.by + r20 * in.bz;
+        const L gy = r01 * in.bx + r11 * in.by + r21 * in.bz;
+        const L gz = r02 * in.bx + r12 * in.by + r22 * in.bz;
+        const L tx = -(ma * (d2s + h2s) * gx), ty = -(ma * (w2s + h2s) * gy), tz = -(ma * (w2s + d2s) * gz);
+        t.tam[0] = r00 * tx + r01 * ty + r02 * tz;
+        t.tam[1] = r10 * tx + r11 * ty + r12 * tz;
+        t.tam[2] = r20 * tx + r21 * ty + r22 * tz;
+    }
+
+    t.cob[0] = cobx; t.cob[1] = coby; t.cob[2] = cobz;
+    t.cop[0] = copx; t.cop[1] = copy; t.cop[2] = copz;
+}
+
+// Net wrench + safety clamp (hydrodynamics_behavior.py:212-226).
+// Lever arms are already body-relative, so  (cob - p) x F_b  =  cob_rel x (0,0,fbz).
+// Only F_z mixes the H-precision buoyancy with the L terms.
+template <typename H, typename L>
+H2O_HD void net_wrench(const Terms<H, L>& t, L mass, L F[3], L T[3], bool& clamped)
+{
+    F[0] = (t.fd[0] + t.fl[0]) + t.fam[0];
+    F[1] = (t.fd[1] + t.fl[1]) + t.fam[1];
+    F[2] = L(t.fbz + H((t.fd[2] + t.fl[2]) + t.fam[2]));
+
+    const L fb = L(t.fbz);
+    const L cx = t.cop[0], cy = t.cop[1], cz = t.cop[2];
+    T[0] = ((t.cob[1] * fb + t.tarm[0]) + (cy * t.fl[2] - cz * t.fl[1])) + (t.td[0] + t.tam[0]);
+    T[1] = ((t.tarm[1] - t.cob[0] * fb) + (cz * t.fl[0] - cx * t.fl[2])) + (t.td[1] + t.tam[1]);
+    T[2] = (t.tarm[2] + (cx * t.fl[1] - cy * t.fl[0])) + (t.td[2] + t.tam[2]);
+
+    // scale = min(1, m*500 / (|F| + 1e-6)); the division only matters when the clamp bites.
+    const L max_force = mass * L(500.0);
+    const L mag2 = F[0] * F[0] + F[1] * F[1] + F[2] * F[2];
+    const L lim = max_force - L(1e-6);
+    clamped = !(lim > L(0)) || mag2 > lim * lim;
+    if (clamped) {
+        const L mag = h2o_sqrt_from_rsqrt(mag2, h2o_rsqrt(h2o_max(mag2, L(1e-30))));
+        const L scale = h2o_min(L(1), max_force * h2o_rcp(mag + L(1e-6)));
+        clamped = scale < L(1);
+        for (int k = 0; k < 3; ++k) {
+            F[k] *= scale;
+            T[k] *= scale;
+        }
+    }
+}
+
+}  // namespace h2o

@@ -1,0 +1,81 @@
+// Host-side instantiation of silver2_isaacsim_b200/csrc/h2o_model.cuh.
+//
+// TEST TOOL ONLY: lets the CPU-only test suite exercise the exact per-body
+// arithmetic the CUDA kernels inline (same header, same precision policies)
+// against the oracle, without a GPU.  It is not part of the package, is not
+// loaded by any product module and is not a fallback path.
+#include <cstdint>
+#include <cstring>
+
+#include "../../silver2_isaacsim_b200/csrc/h2o_model.cuh"
+
+using namespace h2o;
+
+template <typename S, typename H, typename L, bool kExactTrig>
+static void run(int64_t n, const double* pos, const double* quat, const double* v, const double* w,
+                const double* pl, const double* pa, const double* coeff, double rho, double g,
+                double dt, double* F, double* T, double* comp, uint32_t* masks)
+{
+    const L inv_dt = L(1.0 / dt);
+    for (int64_t i = 0; i < n; ++i) {
+        BodyIn<H, L> in;
+        in.pz = H(S(pos[3 * i + 2]));
+        in.qx = H(S(quat[4 * i + 0])); in.qy = H(S(quat[4 * i + 1]));
+        in.qz = H(S(quat[4 * i + 2])); in.qw = H(S(quat[4 * i + 3]));
+        const L vx = L(S(v[3 * i])), vy = L(S(v[3 * i + 1])), vz = L(S(v[3 * i + 2]));
+        const L wx = L(S(w[3 * i])), wy = L(S(w[3 * i + 1])), wz = L(S(w[3 * i + 2]));
+        in.vx = vx; in.vy = vy; in.vz = vz;
+        in.wx = wx; in.wy = wy; in.wz = wz;
+        in.ax = (vx - L(S(pl[3 * i]))) * inv_dt;
+        in.ay = (vy - L(S(pl[3 * i + 1]))) * inv_dt;
+        in.az = (vz - L(S(pl[3 * i + 2]))) * inv_dt;
+        in.bx = (wx - L(S(pa[3 * i]))) * inv_dt;
+        in.by = (wy - L(S(pa[3 * i + 1]))) * inv_dt;
+        in.bz = (wz - L(S(pa[3 * i + 2]))) * inv_dt;
+        const double* c = coeff + 11 * i;
+        in.dimx = L(S(c[0])); in.dimy = L(S(c[1])); in.dimz = L(S(c[2]));
+        in.c_drag = L(S(c[3])); in.c_drag_ang = L(S(c[4]));
+        in.k_damp = L(S(c[5])); in.k_damp_ang = L(S(c[6]));
+        in.c_am = L(S(c[7])); in.c_am_ang = L(S(c[8])); in.c_lift = L(S(c[9]));
+        in.rho_h = H(rho); in.grav_h = H(g); in.rho = L(rho);
+        Terms<H, L> t;
+        body_terms<H, L, kExactTrig>(in, t);
+        L f[3], tq[3];
+        bool clamped;
+        net_wrench<H, L>(t, L(S(c[10])), f, tq, clamped);
+        for (int k = 0; k < 3; ++k) {
+            F[3 * i + k] = double(S(f[k]));
+            T[3 * i + k] = double(S(tq[k]));
+        }
+        if (comp) {
+            double* o = comp + 28 * i;
+            o[0] = 0; o[1] = 0; o[2] = double(t.fbz);
+            for (int k = 0; k < 3; ++k) {
+                o[3 + k] = double(t.fd[k]); o[6 + k] = double(t.fl[k]); o[9 + k] = double(t.td[k]);
+                o[12 + k] = double(t.fam[k]); o[15 + k] = double(t.tam[k]);
+                o[18 + k] = double(t.cob[k]); o[21 + k] = double(t.cop[k]);
+            }
+            o[24] = double(t.ratio);
+            for (int k = 0; k < 3; ++k) o[25 + k] = double(t.tarm[k]);
+        }
+        if (masks) masks[i] = t.kp_mask;
+    }
+}
+
+extern "C" __attribute__((visibility("default")))
+int emul_step(int mode, int exact_trig, int64_t n, const double* pos, const double* quat,
+              const double* v, const double* w, const double* pl, const double* pa,
+              const double* coeff, double rho, double g, double dt, double* F, double* T,
+              double* comp, uint32_t* masks)
+{
+#define GO(S, H, L)                                                                             \
+    (exact_trig ? run<S, H, L, true>(n, pos, quat, v, w, pl, pa, coeff, rho, g, dt, F, T, comp, masks) \
+                : run<S, H, L, false>(n, pos, quat, v, w, pl, pa, coeff, rho, g, dt, F, T, comp, masks))
+    switch (mode) {
+        case 0: GO(double, double, double); return 0;   // fp64 mode
+        case 1: GO(float, double, float); return 0;     // fp32 mode (mixed policy)
+        case 2: GO(float, float, float); return 0;      // all-fp32 (for comparison only)
+        case 3: GO(float, double, double); return 0;    // fp32 storage, all-fp64 arithmetic
+    }
+    return 1;
+}

@@ -1,0 +1,64 @@
+"""C-ABI library: loads, exports every declared symbol, fails loudly without a device."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    names = []
+    for hdr in ("h2o.h", "h2o_dlpack.h"):
+        text = open(os.path.join(ROOT, "include", hdr)).read()
+        names += re.findall(r"H2O_API\s+[\w\s\*]+?\b(h2o_\w+)\s*\(", text)
+    return sorted(set(names))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    declared = _declared_symbols()
+    assert len(declared) >= 38
+    for name in declared:
+        assert hasattr(built_lib, name), f"{name} declared in include/*.h but not exported"
+    from silver2_isaacsim_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared  # the ctypes table binds exactly the declared ABI
+
+
+def test_no_torch_or_cxx_types_in_the_abi():
+    for hdr in ("h2o.h", "h2o_dlpack.h"):
+        text = open(os.path.join(ROOT, "include", hdr)).read()
+        assert "torch" not in text.replace("torch.cuda.current_stream", "").replace("torch.utils.dlpack", "") \
+            .replace("wp.from_torch", "").replace("(Python/PyTorch)", "").replace("wraps torch memory", "") \
+            .replace("C++/torch types", "")
+        assert "std::" not in text and "at::" not in text
+
+
+def test_bad_handle_and_messages(built_lib):
+    assert built_lib.h2o_destroy(None) == 1  # H2O_ERR_BAD_HANDLE
+    assert b"invalid" in built_lib.h2o_last_error()
+    assert built_lib.h2o_version().startswith(b"h2o_b200")
+    assert built_lib.h2o_n_bodies(None) == -1
+
+
+def test_create_fails_loudly_without_gpu(built_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = ctypes.c_void_p()
+    rc = built_lib.h2o_create(ctypes.byref(h), 16, 0, 0)
+    assert rc == 10 and not h.value  # H2O_ERR_NO_DEVICE
+    assert b"no CPU path" in built_lib.h2o_last_error()
+    from silver2_isaacsim_b200 import HydroEngine, H2OError
+    with pytest.raises(H2OError):
+        HydroEngine(16)
+
+
+def test_product_never_imports_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py may touch oracle/."""
+    pkg = os.path.join(ROOT, "silver2_isaacsim_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "hydro_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
