@@ -83,6 +83,7 @@ struct h2o_engine {
     void* hp_pin[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaStream_t hp_stream[HOST_PIPE_STREAMS] = {nullptr, nullptr, nullptr};
     cudaEvent_t hp_prev_ready = nullptr;
+    cudaStream_t capture_stream = nullptr;  // graph capture never runs on the caller's (maybe legacy) stream
 };
 
 static h2o_engine* check(h2o_handle h)
@@ -356,6 +357,7 @@ int h2o_destroy(h2o_handle h)
     for (int i = 0; i < HOST_PIPE_STREAMS; ++i)
         if (e->hp_stream[i]) cudaStreamDestroy(e->hp_stream[i]);
     if (e->hp_prev_ready) cudaEventDestroy(e->hp_prev_ready);
+    if (e->capture_stream) cudaStreamDestroy(e->capture_stream);
     if (e->coeff) cudaFree(e->coeff);
     if (e->slot_type) cudaFree(e->slot_type);
     if (e->prev) cudaFree(e->prev);
@@ -650,13 +652,17 @@ int h2o_capture_rollout(h2o_handle h, int n_steps, double dt, h2o_stream stream)
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
     if (e->graph) { cudaGraphDestroy(e->graph); e->graph = nullptr; }
-    // one eager step first so that every per-kernel attribute / occupancy query is done outside capture
+    // One eager step first (on the caller's stream) so that every per-kernel attribute / occupancy
+    // query happens outside capture.  The capture itself runs on an engine-owned stream: the
+    // caller's stream may be the legacy default stream, which cannot be captured.
     const int64_t before0 = e->launches;
     int rc = step_device(e, e->b_layout, e->b_pos, e->b_quat, e->b_lin, e->b_ang, dt, e->b_f, e->b_t, e->b_w, e->n, 0,
                          e->prev, coeff_at(e, 0), s);
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(s));
     const int64_t per_step = e->launches - before0;
+    if (!e->capture_stream) CUDA_TRY(cudaStreamCreateWithFlags(&e->capture_stream, cudaStreamNonBlocking));
+    s = e->capture_stream;
     CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
     for (int i = 0; i < n_steps && rc == H2O_OK; ++i)
         rc = step_device(e, e->b_layout, e->b_pos, e->b_quat, e->b_lin, e->b_ang, dt, e->b_f, e->b_t, e->b_w, e->n, 0,
