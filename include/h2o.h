@@ -107,6 +107,8 @@ H2O_API int h2o_set_articulation(h2o_handle h, int bodies_per_robot);
  * (hydrodynamics_behavior.py:194); the wrappers themselves take xyzw. */
 H2O_API int h2o_set_quat_order(h2o_handle h, int order);
 H2O_API int h2o_set_kernel(h2o_handle h, int choice);
+/* Tuning knob: tile-kernel variant (threads per CTA / TMA stages); 0 = built-in default. */
+H2O_API int h2o_set_tile_config(h2o_handle h, int cfg);
 /* Accumulate global statistics inside the step kernel (device-side, no host sync). */
 H2O_API int h2o_enable_stats(h2o_handle h, int enable);
 
@@ -176,6 +178,8 @@ H2O_API int64_t h2o_n_bodies(h2o_handle h);
 H2O_API int h2o_dtype_of(h2o_handle h);
 /* Which kernel the last step used: H2O_KERNEL_TILE or H2O_KERNEL_DIRECT. */
 H2O_API int h2o_last_kernel(h2o_handle h);
+/* Resident CTAs per SM of the last tile-kernel launch (occupancy query result). */
+H2O_API int h2o_last_ctas_per_sm(h2o_handle h);
 /* Device pointers of engine-owned buffers (zero-copy views for DLPack export on the host side). */
 H2O_API int h2o_prev_device_ptr(h2o_handle h, void** out_ptr);  /* (N,6) */
 H2O_API int h2o_coeff_device_ptr(h2o_handle h, void** out_ptr, int64_t* out_rows); /* (rows,11) */

@@ -53,6 +53,7 @@ SIGNATURES = {
     "h2o_set_articulation": (c_int, [_P, c_int]),
     "h2o_set_quat_order": (c_int, [_P, c_int]),
     "h2o_set_kernel": (c_int, [_P, c_int]),
+    "h2o_set_tile_config": (c_int, [_P, c_int]),
     "h2o_enable_stats": (c_int, [_P, c_int]),
     "h2o_reset": (c_int, [_P, _P]),
     "h2o_set_prev": (c_int, [_P, _P, _P, _P]),
@@ -72,6 +73,7 @@ SIGNATURES = {
     "h2o_n_bodies": (c_int64, [_P]),
     "h2o_dtype_of": (c_int, [_P]),
     "h2o_last_kernel": (c_int, [_P]),
+    "h2o_last_ctas_per_sm": (c_int, [_P]),
     "h2o_prev_device_ptr": (c_int, [_P, POINTER(c_void_p)]),
     "h2o_coeff_device_ptr": (c_int, [_P, POINTER(c_void_p), POINTER(c_int64)]),
     # include/h2o_dlpack.h

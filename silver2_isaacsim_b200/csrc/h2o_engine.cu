@@ -68,6 +68,8 @@ struct h2o_engine {
     int last_kernel = 0;
     int64_t launches = 0;
     int sm_count = 148;
+    int tile_cfg = 0;          // 0 = default configuration of the dtype
+    int last_ctas_per_sm = 0;
     // bound tensors
     bool bound = false;
     int b_layout = LAYOUT_SPLIT;
@@ -114,21 +116,22 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 // ---------------------------------------------------------------------------
 // tile-kernel configurations
 // ---------------------------------------------------------------------------
-// kThreads bodies per tile, kStagesIn-deep TMA load ring, kStagesOut store buffers.
-template <typename S> struct TileCfg;
-template <> struct TileCfg<float> {
-    static constexpr int kThreads = 256, kIn = 2, kOut = 2;
+// T bodies per tile (= threads per CTA), I-deep TMA load ring, O store buffers,
+// MB = minimum CTAs per SM promised to the compiler (register budget).
+template <int T, int I, int O, int MB, bool CO = false> struct Cfg {
+    static constexpr int kThreads = T, kIn = I, kOut = O, kMinBlocks = MB;
+    static constexpr bool kCopyOnly = CO;  // measurement aid: memory traffic without arithmetic
 };
-template <> struct TileCfg<double> {
-    static constexpr int kThreads = 128, kIn = 2, kOut = 2;
-};
+template <typename S> struct DefaultCfg;
+template <> struct DefaultCfg<float> { using type = Cfg<128, 1, 2, 6>; };
+template <> struct DefaultCfg<double> { using type = Cfg<64, 1, 2, 6>; };
 
-template <typename S, int kLayout, int kParam, bool kRobot, bool kStats> struct TileLaunch {
-    using C = TileCfg<S>;
+template <typename S, int kLayout, int kParam, bool kRobot, bool kStats, typename C> struct TileLaunch {
     using SM = TileSmem<S, kLayout, kParam, C::kThreads, C::kIn, C::kOut>;
     static auto kernel()
     {
-        return &step_tile_kernel<S, kLayout, kParam, kRobot, kStats, C::kThreads, C::kIn, C::kOut>;
+        return &step_tile_kernel<S, kLayout, kParam, kRobot, kStats, C::kThreads, C::kIn, C::kOut, C::kMinBlocks,
+                                 C::kCopyOnly>;
     }
     static size_t smem() { return SM::total(kRobot); }
     static cudaError_t prepare(int* ctas_per_sm)
@@ -143,20 +146,19 @@ template <typename S, int kLayout, int kParam, bool kRobot, bool kStats> struct 
 static long long gcd_ll(long long a, long long b) { return b ? gcd_ll(b, a % b) : a; }
 
 // bodies per tile: multiple of the 16-byte element granule and of bodies_per_robot
-template <typename S> static int tile_bodies_for(int bodies_per_robot)
+static int tile_bodies_for(int threads, size_t esz, int bodies_per_robot)
 {
-    const int T = TileCfg<S>::kThreads;
-    const int granule = int(16 / sizeof(S));  // 4 (fp32) or 2 (fp64) bodies keep every stream 16B-aligned
-    if (bodies_per_robot <= 0) return T;
+    const int granule = int(16 / esz);  // 4 (fp32) or 2 (fp64) bodies keep every stream 16B-aligned
+    if (bodies_per_robot <= 0) return threads;
     const long long l = (long long)granule / gcd_ll(granule, bodies_per_robot) * bodies_per_robot;
-    if (l > T) return 0;  // robot does not fit a tile: fused reduction unavailable
-    return int(T / l * l);
+    if (l > threads) return 0;  // robot does not fit a tile: fused reduction unavailable
+    return int(threads / l * l);
 }
 
-template <typename S, int kLayout, int kParam, bool kRobot, bool kStats>
-static int launch_tile(h2o_engine* e, const StepArgs& a, cudaStream_t stream)
+template <typename S, int kLayout, int kParam, bool kRobot, bool kStats, typename C>
+static int launch_tile(h2o_engine* e, StepArgs& a, cudaStream_t stream)
 {
-    using TLn = TileLaunch<S, kLayout, kParam, kRobot, kStats>;
+    using TLn = TileLaunch<S, kLayout, kParam, kRobot, kStats, C>;
     static int ctas_per_sm[16] = {0};
     int dev = e->device & 15;
     if (ctas_per_sm[dev] == 0) {
@@ -165,10 +167,13 @@ static int launch_tile(h2o_engine* e, const StepArgs& a, cudaStream_t stream)
         if (c < 1) return fail(H2O_ERR_CUDA, "tile kernel does not fit on an SM (smem %zu)", TLn::smem());
         ctas_per_sm[dev] = c;
     }
+    a.tile_bodies = tile_bodies_for(C::kThreads, sizeof(S), kRobot ? a.bodies_per_robot : 0);
+    a.n_tiles = int(std::min<long long>(a.n / a.tile_bodies, 0x7fffffff));
     const int grid = std::min<long long>(a.n_tiles, (long long)e->sm_count * ctas_per_sm[dev]);
-    TLn::kernel()<<<grid, TLn::C::kThreads, TLn::smem(), stream>>>(a);
+    TLn::kernel()<<<grid, C::kThreads, TLn::smem(), stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     e->launches += 1;
+    e->last_ctas_per_sm = ctas_per_sm[dev];
     return H2O_OK;
 }
 
@@ -200,8 +205,9 @@ static int launch_robot_wrench(h2o_engine* e, const StepArgs& a, long long robot
 template <typename S, int kLayout, int kParam, bool kStats>
 static int step_typed2(h2o_engine* e, StepArgs& a, cudaStream_t stream)
 {
+    using DC = typename DefaultCfg<S>::type;
     const bool robots = a.bodies_per_robot > 0 && a.out_wrench != nullptr;
-    const int TB = tile_bodies_for<S>(robots ? a.bodies_per_robot : 0);
+    const int TB = tile_bodies_for(DC::kThreads, sizeof(S), robots ? a.bodies_per_robot : 0);
     bool ptr_ok = aligned16(a.pos) && aligned16(a.lin) && aligned16(a.prev) && aligned16(a.out_force) &&
                   aligned16(a.out_torque) && (kLayout == LAYOUT_PHYSX || (aligned16(a.quat) && aligned16(a.ang))) &&
                   (kParam == PARAM_TABLE || aligned16(a.coeff));
@@ -212,12 +218,38 @@ static int step_typed2(h2o_engine* e, StepArgs& a, cudaStream_t stream)
 
     long long done_bodies = 0;
     if (use_tile) {
-        a.tile_bodies = TB;
-        a.n_tiles = int(std::min<long long>(a.n / TB, 0x7fffffff));
-        int rc = robots ? launch_tile<S, kLayout, kParam, true, kStats>(e, a, stream)
-                        : launch_tile<S, kLayout, kParam, false, kStats>(e, a, stream);
+        int rc;
+        constexpr bool kTunable = sizeof(S) == 4 && kLayout == LAYOUT_SPLIT && kParam == PARAM_PER_BODY && !kStats;
+        bool launched = false;
+        if constexpr (kTunable) {
+          if (!robots && e->tile_cfg != 0) {
+            // tuning variants (h2o_set_tile_config), fp32 / split layout / per-body records only
+            launched = true;
+            switch (e->tile_cfg) {
+#define H2O_CFG(ID, T, I, O, MB) \
+    case ID: rc = launch_tile<S, kLayout, kParam, false, kStats, Cfg<T, I, O, MB>>(e, a, stream); break;
+                H2O_CFG(1, 256, 2, 2, 2)
+                H2O_CFG(2, 256, 1, 2, 3)
+                H2O_CFG(3, 128, 2, 2, 5)
+                H2O_CFG(4, 128, 1, 2, 6)
+                H2O_CFG(5, 128, 1, 2, 7)
+                H2O_CFG(6, 128, 1, 2, 8)
+                H2O_CFG(7, 64, 1, 2, 12)
+                H2O_CFG(8, 64, 2, 2, 12)
+                H2O_CFG(9, 96, 1, 2, 9)
+#undef H2O_CFG
+                case 10: rc = launch_tile<S, kLayout, kParam, false, kStats, Cfg<128, 1, 2, 6, true>>(e, a, stream); break;
+                case 11: rc = launch_tile<S, kLayout, kParam, false, kStats, Cfg<256, 2, 2, 2, true>>(e, a, stream); break;
+                default: return fail(H2O_ERR_BAD_ARGUMENT, "unknown tile config %d", e->tile_cfg);
+            }
+          }
+        }
+        if (!launched) {
+            rc = robots ? launch_tile<S, kLayout, kParam, true, kStats, DC>(e, a, stream)
+                        : launch_tile<S, kLayout, kParam, false, kStats, DC>(e, a, stream);
+        }
         if (rc) return rc;
-        done_bodies = (long long)a.n_tiles * TB;
+        done_bodies = (long long)a.n_tiles * a.tile_bodies;
         e->last_kernel = H2O_KERNEL_TILE;
     } else {
         e->last_kernel = H2O_KERNEL_DIRECT;
@@ -492,6 +524,15 @@ int h2o_set_kernel(h2o_handle h, int choice)
     if (!e) return H2O_ERR_BAD_HANDLE;
     if (choice < H2O_KERNEL_AUTO || choice > H2O_KERNEL_DIRECT) return fail(H2O_ERR_BAD_ARGUMENT, "bad kernel choice");
     e->kernel_choice = choice;
+    return H2O_OK;
+}
+
+int h2o_set_tile_config(h2o_handle h, int cfg)
+{
+    h2o_engine* e = check(h);
+    if (!e) return H2O_ERR_BAD_HANDLE;
+    if (cfg < 0 || cfg > 11) return fail(H2O_ERR_BAD_ARGUMENT, "tile config must be in [0,11]");
+    e->tile_cfg = cfg;
     return H2O_OK;
 }
 
@@ -795,7 +836,8 @@ int h2o_step_host(h2o_handle h, const void* pos, const void* quat, const void* l
 
     // chunking: whole tiles / whole robots per chunk, a few chunks per stream
     const int bpr = (out_robot_wrench && e->bodies_per_robot > 0) ? e->bodies_per_robot : 0;
-    long long unit = e->dtype == H2O_F32 ? tile_bodies_for<float>(bpr) : tile_bodies_for<double>(bpr);
+    long long unit = e->dtype == H2O_F32 ? tile_bodies_for(DefaultCfg<float>::type::kThreads, 4, bpr)
+                                         : tile_bodies_for(DefaultCfg<double>::type::kThreads, 8, bpr);
     if (unit <= 0) unit = bpr > 0 ? bpr : 256;
     if (e->n_slots > 1) unit = unit / gcd_ll(unit, e->n_slots) * e->n_slots;  // keep slot phase per chunk
     long long chunk = (e->n + 4 * HOST_PIPE_STREAMS - 1) / (4 * HOST_PIPE_STREAMS);
@@ -875,6 +917,11 @@ int h2o_dtype_of(h2o_handle h)
 {
     h2o_engine* e = check(h);
     return e ? e->dtype : -1;
+}
+int h2o_last_ctas_per_sm(h2o_handle h)
+{
+    h2o_engine* e = check(h);
+    return e ? e->last_ctas_per_sm : -1;
 }
 int h2o_last_kernel(h2o_handle h)
 {

@@ -329,10 +329,19 @@ struct TileSmem {
 
 // ---------------------------------------------------------------------------
 // step_tile_kernel
+//
+// Persistent CTAs; CTA c handles tiles c, c+grid, ...  Per tile:
+//   wait(full[stage]) -> every thread pulls its body's 19(+11) scalars from the stage into
+//   registers -> barrier A (stage is free again) -> thread 0 immediately re-arms the stage
+//   with the TMA loads of the tile kIn iterations ahead -> compute -> results into an output
+//   stage -> fence.proxy.async + barrier C -> thread 0 issues the TMA bulk stores.
+// Releasing the input stage before the arithmetic means even a single stage overlaps the
+// next tile's loads with this tile's compute, which keeps shared memory per CTA small and
+// lets many CTAs share an SM (the kernel is issue-bound, so resident warps matter).
 // ---------------------------------------------------------------------------
 template <typename S, int kLayout, int kParam, bool kRobot, bool kStats, int kThreads, int kStagesIn,
-          int kStagesOut>
-__global__ void __launch_bounds__(kThreads) step_tile_kernel(const __grid_constant__ StepArgs a)
+          int kStagesOut, int kMinBlocks, bool kCopyOnly = false>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const __grid_constant__ StepArgs a)
 {
     using TL = TileLayout<S, kLayout, kParam>;
     using SM = TileSmem<S, kLayout, kParam, kThreads, kStagesIn, kStagesOut>;
@@ -386,9 +395,8 @@ __global__ void __launch_bounds__(kThreads) step_tile_kernel(const __grid_consta
     };
 
     const int first = blockIdx.x, stride = gridDim.x;
-    // prologue: fill kStagesIn-1 stages
-    if (tid == 0) {
-        for (int j = 0; j < kStagesIn - 1; ++j) {
+    if (tid == 0) {  // prologue: arm every input stage
+        for (int j = 0; j < kStagesIn; ++j) {
             const int tile = first + j * stride;
             if (tile < a.n_tiles) issue_loads(tile, j);
         }
@@ -398,16 +406,14 @@ __global__ void __launch_bounds__(kThreads) step_tile_kernel(const __grid_consta
     const S inv_dt = S(a.inv_dt);
     const int bpr = a.bodies_per_robot;
     const int robots_per_tile = kRobot ? TB / bpr : 0;
+    const bool active = tid < TB;
 
     int it = 0;
     for (int tile = first; tile < a.n_tiles; tile += stride, ++it) {
         const int stage = it % kStagesIn;
         const int ostage = it % kStagesOut;
-        if (tid == 0) {
-            const int nxt = tile + (kStagesIn - 1) * stride;
-            if (nxt < a.n_tiles) issue_loads(nxt, (it + kStagesIn - 1) % kStagesIn);
-        }
         if (kRobot) {
+            // same thread <-> same index as the read-out loop below: no barrier needed in between
             for (int i = tid; i < robots_per_tile * 6; i += kThreads) robot_acc[i] = 0.0;
         }
         mbar_wait(&full_bar[stage], (it / kStagesIn) & 1);
@@ -421,29 +427,52 @@ __global__ void __launch_bounds__(kThreads) step_tile_kernel(const __grid_consta
         bp.prev = reinterpret_cast<const S*>(in + o_prev);
         bp.coeff = reinterpret_cast<const S*>(in + o_coeff);
 
-        const bool active = tid < TB;
-        S F[3] = {S(0), S(0), S(0)}, T[3] = {S(0), S(0), S(0)};
         RawBody<S> r;
+        S cl[N_COEFF];
+        S basex = S(0), basey = S(0), basez = S(0);
+        int seg = 0;
         if (active) {
             load_raw<S, kLayout>(bp, tid, r);
             const S* c;
             if (kParam == PARAM_PER_BODY) {
                 c = bp.coeff + N_COEFF * tid;
             } else {
-                const long long gb = a.first_body + (long long)tile * TB + tid;
-                c = table + N_COEFF * int(slot_map[int(gb % a.n_slots)]);
+                int slot = 0;
+                if (a.n_slots > 1) {
+                    const int base_mod = int((a.first_body + (long long)tile * TB) % a.n_slots);
+                    slot = (base_mod + tid) % a.n_slots;
+                }
+                c = table + N_COEFF * int(slot_map[slot]);
             }
-            BodyIn<double, S> bin;
-            make_body_in<S>(r, c, a.quat_wxyz, a.rho, a.grav, inv_dt, bin);
-            body_step<S>(bin, c[10], F, T, kStats ? &st : nullptr);
+#pragma unroll
+            for (int k = 0; k < N_COEFF; ++k) cl[k] = c[k];
+            if (kRobot) {
+                seg = tid / bpr;
+                const S* pb = bp.pos + TL::E_POS * (seg * bpr);
+                basex = pb[0]; basey = pb[1]; basez = pb[2];
+            }
         }
-
         // the bulk store that last used this output stage must have finished reading it
         if (tid == 0) bulk_wait_read<kStagesOut - 1>();
-        __syncthreads();
+        __syncthreads();  // (A) input stage consumed, output stage free
+        if (tid == 0) {
+            const int nxt = tile + kStagesIn * stride;
+            if (nxt < a.n_tiles) issue_loads(nxt, stage);
+        }
 
+        S F[3] = {S(0), S(0), S(0)}, T[3] = {S(0), S(0), S(0)};
         unsigned char* out = smem + SM::OFF_OUT + size_t(ostage) * SM::OUT_BYTES;
         if (active) {
+            if (kCopyOnly) {
+                // measurement aid (tile config 10): same memory traffic, no arithmetic
+                F[0] = r.px + cl[0]; F[1] = r.py + cl[3]; F[2] = r.pz + cl[6];
+                T[0] = r.q0 + cl[9]; T[1] = r.q1 + r.q2 + r.pvx + r.pvz; T[2] = r.q3 + cl[10] + r.pwy;
+            } else {
+                BodyIn<double, S> bin;
+                make_body_in<S>(r, cl, a.quat_wxyz, a.rho, a.grav, inv_dt, bin);
+                body_step<S>(bin, cl[10], F, T, kStats ? &st : nullptr);
+            }
+
             using V2 = typename Vec2Of<S>::type;
             S* of = reinterpret_cast<S*>(out) + 3 * tid;
             S* ot = reinterpret_cast<S*>(out + oo_t) + 3 * tid;
@@ -458,12 +487,9 @@ __global__ void __launch_bounds__(kThreads) step_tile_kernel(const __grid_consta
         if (kRobot) {
             // wrench about the robot's slot-0 body: tau_i + (p_i - p_base) x F_i
             double v[6] = {0, 0, 0, 0, 0, 0};
-            int seg = 0;
             if (active) {
-                seg = tid / bpr;
-                const S* pb = bp.pos + TL::E_POS * (seg * bpr);
-                const double ax = double(r.px) - double(pb[0]), ay = double(r.py) - double(pb[1]),
-                             az = double(r.pz) - double(pb[2]);
+                const double ax = double(r.px) - double(basex), ay = double(r.py) - double(basey),
+                             az = double(r.pz) - double(basez);
                 const double fx = double(F[0]), fy = double(F[1]), fz = double(F[2]);
                 v[0] = fx; v[1] = fy; v[2] = fz;
                 v[3] = double(T[0]) + (ay * fz - az * fy);
@@ -473,7 +499,7 @@ __global__ void __launch_bounds__(kThreads) step_tile_kernel(const __grid_consta
             robot_reduce_warp(v, seg, active, robot_acc);
         }
         fence_proxy_async_smem();
-        __syncthreads();
+        __syncthreads();  // (C) results (and robot accumulators) complete
 
         if (tid == 0) {
             const long long b0 = (long long)tile * TB;
@@ -485,7 +511,6 @@ __global__ void __launch_bounds__(kThreads) step_tile_kernel(const __grid_consta
         if (kRobot) {
             S* ow = reinterpret_cast<S*>(a.out_wrench) + ((long long)tile * robots_per_tile) * 6;
             for (int i = tid; i < robots_per_tile * 6; i += kThreads) ow[i] = S(robot_acc[i]);
-            __syncthreads();  // robot_acc is re-zeroed at the top of the next iteration
         }
     }
     if (tid == 0) bulk_wait_all<0>();

@@ -157,6 +157,14 @@ class HydroEngine:
         code = {"auto": L.H2O_KERNEL_AUTO, "tile": L.H2O_KERNEL_TILE, "direct": L.H2O_KERNEL_DIRECT}[choice]
         L.check(self._lib.h2o_set_kernel(self._h, code))
 
+    def set_tile_config(self, cfg: int = 0):
+        """Tuning knob: tile-kernel variant (0 = default)."""
+        L.check(self._lib.h2o_set_tile_config(self._h, int(cfg)))
+
+    @property
+    def ctas_per_sm(self) -> int:
+        return int(self._lib.h2o_last_ctas_per_sm(self._h))
+
     def enable_stats(self, enable: bool = True):
         L.check(self._lib.h2o_enable_stats(self._h, int(bool(enable))))
 

