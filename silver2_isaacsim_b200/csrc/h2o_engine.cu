@@ -69,6 +69,9 @@ struct h2o_engine {
     int64_t launches = 0;
     int sm_count = 148;
     int tile_cfg = 0;          // 0 = default configuration of the dtype
+    bool balance_tiles = false;  // see launch_tile: only pays when the kernel is not issue-bound
+    int max_ctas_per_sm = 0;   // 0 = as many as fit
+    bool use_pdl = false;      // programmatic dependent launch of the tile kernel
     int last_ctas_per_sm = 0;
     // bound tensors
     bool bound = false;
@@ -145,12 +148,19 @@ template <typename S, int kLayout, int kParam, bool kRobot, bool kStats, typenam
 
 static long long gcd_ll(long long a, long long b) { return b ? gcd_ll(b, a % b) : a; }
 
-// bodies per tile: multiple of the 16-byte element granule and of bodies_per_robot
+// smallest tile granule: 4 (fp32) or 2 (fp64) bodies keep every stream 16-byte aligned;
+// with an articulation a tile must also hold whole robots
+static long long tile_unit(size_t esz, int bodies_per_robot)
+{
+    const long long granule = (long long)(16 / esz);
+    if (bodies_per_robot <= 0) return granule;
+    return granule / gcd_ll(granule, bodies_per_robot) * bodies_per_robot;
+}
+
+// largest tile (bodies) a CTA of `threads` threads can take
 static int tile_bodies_for(int threads, size_t esz, int bodies_per_robot)
 {
-    const int granule = int(16 / esz);  // 4 (fp32) or 2 (fp64) bodies keep every stream 16B-aligned
-    if (bodies_per_robot <= 0) return threads;
-    const long long l = (long long)granule / gcd_ll(granule, bodies_per_robot) * bodies_per_robot;
+    const long long l = tile_unit(esz, bodies_per_robot);
     if (l > threads) return 0;  // robot does not fit a tile: fused reduction unavailable
     return int(threads / l * l);
 }
@@ -167,13 +177,43 @@ static int launch_tile(h2o_engine* e, StepArgs& a, cudaStream_t stream)
         if (c < 1) return fail(H2O_ERR_CUDA, "tile kernel does not fit on an SM (smem %zu)", TLn::smem());
         ctas_per_sm[dev] = c;
     }
-    a.tile_bodies = tile_bodies_for(C::kThreads, sizeof(S), kRobot ? a.bodies_per_robot : 0);
+    // Balanced tiling: the largest tile that fits a CTA would leave a ragged last round
+    // (e.g. 8192 tiles over 888 resident CTAs = 9.2 rounds -> a 10th round with 22 % of the CTAs
+    // busy).  Shrink the tile so that every resident CTA runs the same number of rounds.
+    const int tb_max = tile_bodies_for(C::kThreads, sizeof(S), kRobot ? a.bodies_per_robot : 0);
+    int cps = ctas_per_sm[dev];
+    if (e->max_ctas_per_sm > 0) cps = std::min(cps, e->max_ctas_per_sm);
+    const long long slots = (long long)e->sm_count * cps;
+    int tb = tb_max;
+    if (e->balance_tiles && a.n > slots * tb_max) {
+        const long long rounds = (a.n + slots * tb_max - 1) / (slots * tb_max);
+        const long long unit = tile_unit(sizeof(S), kRobot ? a.bodies_per_robot : 0);
+        long long want = (a.n + slots * rounds - 1) / (slots * rounds);
+        want = (want + unit - 1) / unit * unit;
+        if (want >= unit && want <= tb_max) tb = int(want);
+    }
+    a.tile_bodies = tb;
     a.n_tiles = int(std::min<long long>(a.n / a.tile_bodies, 0x7fffffff));
-    const int grid = std::min<long long>(a.n_tiles, (long long)e->sm_count * ctas_per_sm[dev]);
-    TLn::kernel()<<<grid, C::kThreads, TLn::smem(), stream>>>(a);
+    const int grid = int(std::min<long long>(a.n_tiles, slots));
+    if (e->use_pdl) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(C::kThreads);
+        cfg.dynamicSmemBytes = TLn::smem();
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, TLn::kernel(), a));
+    } else {
+        TLn::kernel()<<<grid, C::kThreads, TLn::smem(), stream>>>(a);
+    }
     CUDA_TRY(cudaGetLastError());
     e->launches += 1;
-    e->last_ctas_per_sm = ctas_per_sm[dev];
+    e->last_ctas_per_sm = cps;
     return H2O_OK;
 }
 
@@ -362,6 +402,9 @@ int h2o_create(h2o_handle* out, int64_t n_bodies, int dtype, int device)
     e->n = n_bodies;
     e->esz = dtype == H2O_F32 ? 4 : 8;
     e->sm_count = prop.multiProcessorCount;
+    if (const char* v = getenv("H2O_BALANCE_TILES")) e->balance_tiles = atoi(v) != 0;
+    if (const char* v = getenv("H2O_MAX_CTAS_PER_SM")) e->max_ctas_per_sm = atoi(v);
+    if (const char* v = getenv("H2O_PDL")) e->use_pdl = atoi(v) != 0;
     if (cudaMalloc(&e->prev, size_t(n_bodies) * 6 * e->esz) != cudaSuccess ||
         cudaMalloc(reinterpret_cast<void**>(&e->stats), N_STATS * sizeof(double)) != cudaSuccess) {
         cudaGetLastError();

@@ -122,6 +122,10 @@ template <int N> __device__ __forceinline__ void bulk_wait_all()
 {
     asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
+// Programmatic dependent launch (PDL): let the next kernel in the stream become resident while
+// this one drains, and make this one wait for its predecessor before touching global memory.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_prerequisites() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -209,14 +213,22 @@ struct ThreadStats {
     unsigned wet = 0, clamped = 0, nonfinite = 0, still = 0, bodies = 0;
 };
 
+// fp32 mode: body-frame fast path; fp64 mode: the world-frame formulation (exact in dq).
 template <typename S>
 __device__ __forceinline__ void body_step(const BodyIn<double, S>& in, S mass, S F[3], S T[3],
                                           ThreadStats* st)
 {
-    Terms<double, S> t;
-    body_terms<double, S, false>(in, t);
-    bool clamped;
-    net_wrench<double, S>(t, mass, F, T, clamped);
+    bool clamped, still;
+    double ratio;
+    if (sizeof(S) == 4) {
+        body_wrench_fast<double, S>(in, mass, F, T, clamped, ratio, still);
+    } else {
+        Terms<double, S> t;
+        body_terms<double, S, false>(in, t);
+        net_wrench<double, S>(t, mass, F, T, clamped);
+        ratio = t.ratio;
+        still = t.still;
+    }
     if (st) {
         const double mag = sqrt(double(F[0]) * double(F[0]) + double(F[1]) * double(F[1]) + double(F[2]) * double(F[2]));
         st->bodies += 1;
@@ -226,9 +238,9 @@ __device__ __forceinline__ void body_step(const BodyIn<double, S>& in, S mass, S
         } else {
             st->nonfinite += 1;
         }
-        st->wet += (t.ratio > 0.0) ? 1u : 0u;
+        st->wet += (ratio > 0.0) ? 1u : 0u;
         st->clamped += clamped ? 1u : 0u;
-        st->still += (t.ratio > 0.0 && t.still) ? 1u : 0u;
+        st->still += (ratio > 0.0 && still) ? 1u : 0u;
     }
 }
 
@@ -368,11 +380,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
     const uint32_t b_f = 3u * TB * sizeof(S);
     const uint32_t oo_t = b_f, oo_prev = 2 * b_f;
 
+    pdl_launch_dependents();  // no-op unless launched with the PDL attribute
     if (tid == 0) {
         for (int s = 0; s < kStagesIn; ++s) mbar_init(&full_bar[s], 1);
         mbar_fence_init();
         fence_proxy_async_smem();
     }
+    pdl_wait_prerequisites();  // everything below reads / writes global memory
     if (kParam == PARAM_TABLE) {
         const S* g = reinterpret_cast<const S*>(a.coeff);
         for (int i = tid; i < a.n_types * N_COEFF; i += kThreads) table[i] = g[i];

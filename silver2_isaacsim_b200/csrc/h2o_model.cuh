@@ -441,4 +441,186 @@ H2O_HD void net_wrench(const Terms<H, L>& t, L mass, L F[3], L T[3], bool& clamp
     }
 }
 
+// ---------------------------------------------------------------------------
+// fp32-mode fast path: net wrench only (fused step), torque assembled in the BODY frame.
+//
+// Same model as body_terms + net_wrench.  In the body frame the box makes most terms trivial:
+// the lift axis is v_hat x z_body = (d1, -d0, 0), the lever arms are the face / keypoint
+// offsets themselves, the added-inertia tensor is diagonal, and a single rotation takes the
+// summed body-frame torque to the world.  It uses R(a x b) = (Ra) x (Rb), exact only for an
+// orthogonal R; the reference's R deviates from that by dq = |q|^2 - 1 (~1e-7 for fp32
+// quaternions), i.e. by one fp32 rounding of each term -- fine for the fp32 tolerance, not for
+// fp64 mode, which keeps the world-frame formulation above.  The one place where dq matters
+// even in fp32 (the cancelling cop x F_d, see body_terms) keeps its first-order dq term.
+// ---------------------------------------------------------------------------
+template <typename H, typename L>
+H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], bool& clamped, H& ratio_out,
+                             bool& still)
+{
+    // ---- waterline in H (identical to body_terms)
+    const H hx2 = in.qx + in.qx, hy2 = in.qy + in.qy, hz2 = in.qz + in.qz;
+    const H r20h = in.qx * hz2 - in.qw * hy2;
+    const H r21h = in.qy * hz2 + in.qw * hx2;
+    const H r22h = H(1) - (in.qx * hx2 + in.qy * hy2);
+    const H dqh = ((in.qx * in.qx + in.qy * in.qy) + (in.qz * in.qz + in.qw * in.qw)) - H(1);
+    const H dxh = H(in.dimx), dyh = H(in.dimy), dzh = H(in.dimz);
+    const H a = r20h * (dxh * H(0.5));
+    const H b = r21h * (dyh * H(0.5));
+    const H c = r22h * (dzh * H(0.5));
+    const H abp = a + b, abm = a - b;
+    const H m = -in.pz;
+    uint32_t mask = 0;
+#define H2O_KP(i, j, k, tval)                                                   \
+    {                                                                           \
+        const H tv = (tval);                                                    \
+        h2o_or_if_less(mask, tv, m, 1u << kp_bit(i, j, k));                     \
+        h2o_or_if_less(mask, -tv, m, 1u << kp_bit(-(i), -(j), -(k)));           \
+    }
+    H2O_KP(1, 0, 0, a)
+    H2O_KP(0, 1, 0, b)
+    H2O_KP(1, 1, 0, abp)
+    H2O_KP(1, -1, 0, abm)
+    H2O_KP(0, 0, 1, c)
+    H2O_KP(1, 0, 1, a + c)
+    H2O_KP(1, 0, -1, a - c)
+    H2O_KP(0, 1, 1, b + c)
+    H2O_KP(0, 1, -1, b - c)
+    H2O_KP(1, 1, 1, abp + c)
+    H2O_KP(1, 1, -1, abp - c)
+    H2O_KP(1, -1, 1, abm + c)
+    H2O_KP(1, -1, -1, abm - c)
+#undef H2O_KP
+    h2o_or_if_less(mask, H(0), m, 1u << kp_bit(0, 0, 0));
+    const H ext = (h2o_abs(a) + h2o_abs(b)) + h2o_abs(c);
+    const H z_min = in.pz - ext, z_max = in.pz + ext;
+    const bool dry = z_min >= H(0);
+    const bool partial = !dry && !(z_max <= H(0));
+    const H total_height = z_max - z_min;
+    H ratio = H(1);
+    if (partial && !(total_height < H(1e-6))) ratio = h2o_min(H(1), -z_min * h2o_rcp_h(total_height));
+    if (dry || !(ratio > H(1e-9))) ratio = H(0);
+    ratio_out = ratio;
+    const L rl = L(ratio);
+    const H fbz = in.rho_h * (ratio * (dxh * dyh * dzh)) * in.grav_h;  // numba_hydrodynamics.py:282
+    const L fb = L(fbz);
+
+    // ---- rotation matrix in L (row 2 from the H values)
+    const L qx = L(in.qx), qy = L(in.qy), qz = L(in.qz), qw = L(in.qw);
+    const L x2 = qx + qx, y2 = qy + qy, z2 = qz + qz;
+    const L wx = qw * x2, wy = qw * y2, wz = qw * z2;
+    const L r00 = (L(1) - qy * y2) - qz * z2, r11 = (L(1) - qx * x2) - qz * z2;
+    const L r01 = qx * y2 - wz, r10 = qx * y2 + wz;
+    const L r02 = qx * z2 + wy, r12 = qy * z2 - wx;
+    const L r20 = L(r20h), r21 = L(r21h), r22 = L(r22h);
+    const L k4 = L(4) * L(dqh);
+
+    const L hx = in.dimx * L(0.5), hy = in.dimy * L(0.5), hz = in.dimz * L(0.5);
+    const L ayz = in.dimy * in.dimz, axz = in.dimx * in.dimz, axy = in.dimx * in.dimy;
+    const L vol = in.dimx * ayz;
+
+    // ---- centre of buoyancy in the body frame: h .* sum(sign)/count
+    const int cnt = h2o_popc(mask);
+    const L cinv = (partial && cnt > 0) ? h2o_rcp(L(cnt)) : L(0);
+    const L cbx = L(h2o_popc(mask & KP_XP) - h2o_popc(mask & KP_XN)) * (cinv * hx);
+    const L cby = L(h2o_popc(mask & KP_YP) - h2o_popc(mask & KP_YN)) * (cinv * hy);
+    const L cbz = L(h2o_popc(mask & KP_ZP) - h2o_popc(mask & KP_ZN)) * (cinv * hz);
+
+    // ---- flow direction, world and body (d = R^T v_hat)
+    const L speed2 = in.vx * in.vx + in.vy * in.vy + in.vz * in.vz;
+    const L rs = h2o_rsqrt(h2o_max(speed2, L(1e-30)));
+    const L speed = h2o_sqrt_from_rsqrt(speed2, rs);
+    const bool moving = speed > L(1e-6);
+    const L inv_speed = moving ? rs : L(0);
+    const L ux = in.vx * inv_speed, uy = in.vy * inv_speed, uz = in.vz * inv_speed;
+    still = !moving && (ratio > H(0));
+    const L d0 = r00 * ux + r10 * uy + r20 * uz;
+    const L d1 = r01 * ux + r11 * uy + r21 * uz;
+    const L d2 = r02 * ux + r12 * uy + r22 * uz;
+
+    // ---- projected area, centre of pressure (body frame) -- see body_terms
+    const uint32_t f0 = (d0 < L(0)) ? (1u << kp_bit(1, 0, 0)) : (1u << kp_bit(-1, 0, 0));
+    const uint32_t f1 = (d1 < L(0)) ? (1u << kp_bit(0, 1, 0)) : (1u << kp_bit(0, -1, 0));
+    const uint32_t f2 = (d2 < L(0)) ? (1u << kp_bit(0, 0, 1)) : (1u << kp_bit(0, 0, -1));
+    const L w0 = (mask & f0) ? L(1) : L(0), w1 = (mask & f1) ? L(1) : L(0), w2 = (mask & f2) ? L(1) : L(0);
+    const L g0 = w0 * d0, g1 = w1 * d1, g2 = w2 * d2;
+    const L area = (h2o_abs(g0) * ayz + h2o_abs(g1) * axz) + h2o_abs(g2) * axy;
+    const bool faces = area > L(1e-6);
+    const L inv_area = faces ? h2o_rcp(area) : L(0);
+    const L ginv = (vol * L(0.5)) * inv_area;
+    const L s0 = -(ginv * g0), s1 = -(ginv * g1), s2 = -(ginv * g2);
+    const L armx = faces ? s0 : cbx, army = faces ? s1 : cby, armz = faces ? s2 : cbz;  // cop - p
+
+    // ---- drag force (world) and its lever-arm torque (body)
+    const L q0 = L(0.5) * in.rho * speed2 * area;
+    const L kd = in.k_damp * h2o_min(L(1), speed * L(5.0));
+    const L gam = (q0 * in.c_drag * inv_speed + kd) * rl;  // F_d = -gam * v
+    const L psi = gam * speed;                              // |F_d| along -v_hat
+    // faces: (cop-p) x F_d = psi (c + 4dq (u(u.d) - |u|^2 d) x s), c = d x s factored so that it
+    // is exactly zero when every opposing face is wet; otherwise the arm is cob: psi (d x cob)
+    const L gd0 = ginv * d0, gd1 = ginv * d1, gd2 = ginv * d2;
+    const L udd = qx * d0 + qy * d1 + qz * d2;
+    const L uu = qx * qx + qy * qy + qz * qz;
+    const L gbx = qx * udd - uu * d0, gby = qy * udd - uu * d1, gbz = qz * udd - uu * d2;
+    const L nf = faces ? L(0) : L(1);
+    const L tdx = (gd1 * d2) * (w1 - w2) + k4 * (gby * s2 - gbz * s1) + nf * (d1 * cbz - d2 * cby);
+    const L tdy = (gd2 * d0) * (w2 - w0) + k4 * (gbz * s0 - gbx * s2) + nf * (d2 * cbx - d0 * cbz);
+    const L tdz = (gd0 * d1) * (w0 - w1) + k4 * (gbx * s1 - gby * s0) + nf * (d0 * cby - d1 * cbx);
+
+    // ---- lift in the body frame: axis = d x z = (d1,-d0,0), dir = axis/|axis| x d
+    const L an2 = d0 * d0 + d1 * d1;
+    const L ra = h2o_rsqrt(h2o_max(an2, L(1e-30)));
+    const L an = an2 * ra;
+    const bool lift_ok = !(speed < L(1e-6)) && !(an < L(1e-6));
+    const L dd = h2o_max(L(-1), h2o_min(L(1), -d2));
+    const L omd = h2o_max(an2 - k4 * (qx * qx + qy * qy), L(1e-30));  // 1 - d^2, well conditioned
+    const L cl = L(2) * dd * (omd * h2o_rsqrt(omd));
+    const L sl = lift_ok ? (q0 * cl * in.c_lift) * (rl * ra) : L(0);
+    const L tl = d2 * sl;
+    const L flx = -(d0 * tl), fly = -(d1 * tl), flz = an2 * sl;  // body frame
+
+    // ---- added mass: force in the world frame, inertia torque in the body frame
+    const L rv = vol * in.rho * rl;
+    const L ml = rv * in.c_am;
+    const L ma = rv * in.c_am_ang;
+    const L w2s = in.dimx * in.dimx, d2s = in.dimy * in.dimy, h2s = in.dimz * in.dimz;
+    const L bbx = r00 * in.bx + r10 * in.by + r20 * in.bz;
+    const L bby = r01 * in.bx + r11 * in.by + r21 * in.bz;
+    const L bbz = r02 * in.bx + r12 * in.by + r22 * in.bz;
+
+    // ---- body-frame torque: cob x (fb R^T z) + psi*(...) + arm x F_l + added inertia
+    const L tbx = psi * tdx + (fb * (cby * r22 - cbz * r21) + ((army * flz - armz * fly) - ma * (d2s + h2s) * bbx));
+    const L tby = psi * tdy + (fb * (cbz * r20 - cbx * r22) + ((armz * flx - armx * flz) - ma * (w2s + h2s) * bby));
+    const L tbz = psi * tdz + (fb * (cbx * r21 - cby * r20) + ((armx * fly - army * flx) - ma * (w2s + d2s) * bbz));
+
+    // ---- angular drag (world): -(0.5 rho |w| C V + k min(1, 5|w|)) ratio * w
+    const L as2 = in.wx * in.wx + in.wy * in.wy + in.wz * in.wz;
+    const L as = h2o_sqrt_from_rsqrt(as2, h2o_rsqrt(h2o_max(as2, L(1e-30))));
+    const L aq = (as > L(1e-6)) ? L(0.5) * in.rho * as * in.c_drag_ang * vol : L(0);
+    const L ka = (aq + in.k_damp_ang * h2o_min(L(1), as * L(5.0))) * rl;
+
+    T[0] = (r00 * tbx + r01 * tby + r02 * tbz) - ka * in.wx;
+    T[1] = (r10 * tbx + r11 * tby + r12 * tbz) - ka * in.wy;
+    T[2] = (r20 * tbx + r21 * tby + r22 * tbz) - ka * in.wz;
+
+    F[0] = (r00 * flx + r01 * fly + r02 * flz) - (gam * in.vx + ml * in.ax);
+    F[1] = (r10 * flx + r11 * fly + r12 * flz) - (gam * in.vy + ml * in.ay);
+    const L fz = (r20 * flx + r21 * fly + r22 * flz) - (gam * in.vz + ml * in.az);
+    F[2] = L(fbz + H(fz));
+
+    // ---- safety clamp (hydrodynamics_behavior.py:221-226)
+    const L max_force = mass * L(500.0);
+    const L mag2 = F[0] * F[0] + F[1] * F[1] + F[2] * F[2];
+    const L lim = max_force - L(1e-6);
+    clamped = !(lim > L(0)) || mag2 > lim * lim;
+    if (clamped) {
+        const L mag = h2o_sqrt_from_rsqrt(mag2, h2o_rsqrt(h2o_max(mag2, L(1e-30))));
+        const L scale = h2o_min(L(1), max_force * h2o_rcp(mag + L(1e-6)));
+        clamped = scale < L(1);
+        for (int k = 0; k < 3; ++k) {
+            F[k] *= scale;
+            T[k] *= scale;
+        }
+    }
+}
+
 }  // namespace h2o

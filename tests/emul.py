@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "tests", "_emul", "libh2o_emul.so")
 SRC = os.path.join(ROOT, "tests", "host_emul", "emul.cpp")
 HDR = os.path.join(ROOT, "silver2_isaacsim_b200", "csrc", "h2o_model.cuh")
-MODE_FP64, MODE_FP32, MODE_ALL_FP32, MODE_FP32_STORE_FP64_MATH = 0, 1, 2, 3
+MODE_FP64, MODE_FP32, MODE_ALL_FP32, MODE_FP32_STORE_FP64_MATH, MODE_FP32_FAST = 0, 1, 2, 3, 4
 _lib = None
 
 

@@ -11,7 +11,7 @@
 
 using namespace h2o;
 
-template <typename S, typename H, typename L, bool kExactTrig>
+template <typename S, typename H, typename L, bool kExactTrig, bool kFast = false>
 static void run(int64_t n, const double* pos, const double* quat, const double* v, const double* w,
                 const double* pl, const double* pa, const double* coeff, double rho, double g,
                 double dt, double* F, double* T, double* comp, uint32_t* masks)
@@ -39,10 +39,18 @@ static void run(int64_t n, const double* pos, const double* quat, const double* 
         in.c_am = L(S(c[7])); in.c_am_ang = L(S(c[8])); in.c_lift = L(S(c[9]));
         in.rho_h = H(rho); in.grav_h = H(g); in.rho = L(rho);
         Terms<H, L> t;
-        body_terms<H, L, kExactTrig>(in, t);
         L f[3], tq[3];
         bool clamped;
-        net_wrench<H, L>(t, L(S(c[10])), f, tq, clamped);
+        if (kFast) {
+            H ratio;
+            bool still;
+            body_wrench_fast<H, L>(in, L(S(c[10])), f, tq, clamped, ratio, still);
+            comp = nullptr;
+            t.kp_mask = 0;
+        } else {
+            body_terms<H, L, kExactTrig>(in, t);
+            net_wrench<H, L>(t, L(S(c[10])), f, tq, clamped);
+        }
         for (int k = 0; k < 3; ++k) {
             F[3 * i + k] = double(S(f[k]));
             T[3 * i + k] = double(S(tq[k]));
@@ -76,6 +84,8 @@ int emul_step(int mode, int exact_trig, int64_t n, const double* pos, const doub
         case 1: GO(float, double, float); return 0;     // fp32 mode (mixed policy)
         case 2: GO(float, float, float); return 0;      // all-fp32 (for comparison only)
         case 3: GO(float, double, double); return 0;    // fp32 storage, all-fp64 arithmetic
+        case 4: run<float, double, float, false, true>(n, pos, quat, v, w, pl, pa, coeff, rho, g, dt, F, T, comp, masks);
+                return 0;                               // fp32 mode, fused-step fast path (body frame)
     }
     return 1;
 }
