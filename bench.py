@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--kernel", default="auto", choices=["auto", "tile", "direct"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of graph replay")
+    ap.add_argument("--no-soak", action="store_true", help="skip the 1.2 s clock soak (used for the ncu launch-list pass)")
     ap.add_argument("--no-extra", action="store_true", help="skip the C2/C5/fp64 side measurements")
     ap.add_argument("--cpu-sample", type=int, default=1 << 20)
     return ap.parse_args()
@@ -351,7 +352,7 @@ def run_b200(args):
     if sampler:
         sampler.load_from = time.perf_counter()
     soak_t0 = time.perf_counter()
-    while time.perf_counter() - soak_t0 < 1.2:
+    while not args.no_soak and time.perf_counter() - soak_t0 < 1.2:
         for i in range(200):
             batches[i % len(batches)][0].step_bound(dt)
         torch.cuda.synchronize(dev)
