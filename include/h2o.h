@@ -147,7 +147,17 @@ H2O_API int h2o_step_bound(h2o_handle h, double dt, h2o_stream stream);
  * replayed with one launch (the reference captures a single dim=1 kernel,
  * warp_hydrodynamics_wrapper.py:101-120). */
 H2O_API int h2o_capture_rollout(h2o_handle h, int n_steps, double dt, h2o_stream stream);
+/* Rollout mode: 0 = static state (force-only rollout), 1 = free bodies: after each step the bound
+ * pose / velocity tensors are integrated in place by h2o_integrate_free_bodies (split layout). */
+H2O_API int h2o_set_rollout_mode(h2o_handle h, int free_bodies, double gravity);
 H2O_API int h2o_launch_rollout(h2o_handle h, h2o_stream stream);
+
+/* ---- stand-alone free-body stepper (harness; the reference leaves integration to PhysX) ------
+ * Semi-implicit Euler for free boxes (mass and dimensions from the coefficient records, box
+ * inertia, gravity along -z): velocities first, then pose; all four state tensors updated in place. */
+H2O_API int h2o_integrate_free_bodies(h2o_handle h, void* pos, void* quat, void* lin_vel, void* ang_vel,
+                                      const void* force, const void* torque, double dt, double gravity,
+                                      h2o_stream stream);
 
 /* ---- full-signature components --------------------------------------------------------
  * Replaces XHydrodynamicsWrapper.calculate_hydrodynamic_forces

@@ -65,6 +65,8 @@ SIGNATURES = {
     "h2o_step_bound": (c_int, [_P, c_double, _P]),
     "h2o_capture_rollout": (c_int, [_P, c_int, c_double, _P]),
     "h2o_launch_rollout": (c_int, [_P, _P]),
+    "h2o_set_rollout_mode": (c_int, [_P, c_int, c_double]),
+    "h2o_integrate_free_bodies": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_double, c_double, _P]),
     "h2o_components": (c_int, [_P, _P, _P, _P, _P, _P, _P, POINTER(c_void_p), _P, _P, _P]),
     "h2o_step_host": (c_int, [_P, _P, _P, _P, _P, c_double, _P, _P, _P]),
     "h2o_stats_device_ptr": (c_int, [_P, POINTER(c_void_p)]),

@@ -1,0 +1,132 @@
+"""Batched twin of the reference's ``HydrodynamicsBehavior``.
+
+The reference attaches one ``HydrodynamicsBehavior`` to each scripted prim (20 in the main
+scene), each with its own 1-body ``RigidPrimView``, wrapper, graph and ~35 micro-launches
+per physics step (hydrodynamics_behavior.py:143-238).  This class keeps that script's
+life cycle and parameter surface --
+
+    on_init   exposed variables with the reference defaults (:28-46), then the JSON overlay
+              by prim name (:72-112)
+    on_play   ``_setup``: read the parameters back, build the force engine, cache masses (:143-174)
+    physics   ``_on_physics_step(dt)``: skip if dt <= 1e-6 or the view is invalid (:138-141),
+              read poses / velocities, compute, ``apply_forces_and_torques_at_pos`` (:176-234)
+    on_stop   ``_reset`` (:240-245)
+
+-- but for ALL scripted prims through ONE view and ONE fused kernel launch.  It is written
+against the three ``RigidPrimView`` methods the reference uses (``get_world_poses``,
+``get_velocities``, ``apply_forces_and_torques_at_pos`` + ``get_masses`` / ``is_valid``), so it
+runs unchanged inside Isaac Sim and, in tests, against a stand-in view.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import params as P
+from .engine import HydroEngine
+
+
+class BatchedHydrodynamicsBehavior:
+    BEHAVIOR_NS = "hydrodynamicsBehavior"                      # hydrodynamics_behavior.py:26
+    VARIABLES_TO_EXPOSE = [                                      # names/defaults of :28-46
+        {"attr_name": k, "default_value": v} for k, v in P.EXPOSED_VARIABLES
+    ]
+
+    def __init__(self, prim_names: Sequence[str], view, device: str = "cuda:0",
+                 config_path: Optional[str] = None, dtype: torch.dtype = torch.float32,
+                 bodies_per_robot: int = 0):
+        self.prim_names = list(prim_names)
+        self._view = view
+        self._device = device
+        self._dtype = dtype
+        self._config_path = config_path
+        self._bodies_per_robot = int(bodies_per_robot)
+        self._engine: Optional[HydroEngine] = None
+        self._F = self._T = None
+        self.robot_wrench = None
+        self.part_of: List[Optional[str]] = []
+        self.on_init()
+
+    # ------------------------------------------------------------------ life cycle
+    def on_init(self):
+        """Defaults -> JSON ``globals`` -> first matching ``parts`` entry, per prim (:48-112)."""
+        try:
+            config = P.load_config(self._config_path)
+        except (OSError, ValueError):  # "[Hydro] Config missing" / "JSON Error": keep the defaults
+            config = {}
+        self.exposed: Dict[str, P.HydroParams] = {}
+        self.part_of = []
+        for name in self.prim_names:
+            p, part = P.params_for_prim(name, config)
+            self.exposed[name] = p.as_float32()  # USD stores the exposed variables as fp32 Floats
+            self.part_of.append(part)
+        self._config = config
+
+    def set_exposed_variable(self, prim_name: str, attr_name: str, value: float) -> bool:
+        """Edit one exposed variable before play (the property-window path of the reference)."""
+        return self.exposed[prim_name].set(attr_name, np.float32(value))
+
+    def on_play(self):
+        self._setup()
+
+    def on_stop(self):
+        self._reset()
+
+    def on_destroy(self):
+        self._reset()
+
+    # ------------------------------------------------------------------ _setup (:143-174)
+    def _setup(self):
+        n = len(self.prim_names)
+        masses = self._view.get_masses(clone=False)
+        masses = masses.detach().cpu().numpy() if isinstance(masses, torch.Tensor) else np.asarray(masses)
+        first = self.exposed[self.prim_names[0]]
+        rows = []
+        for i, name in enumerate(self.prim_names):
+            p = self.exposed[name]
+            if (p.waterDensity, p.gravity) != (first.waterDensity, first.gravity):
+                raise ValueError("waterDensity / gravity must be the same for every prim of one engine")
+            rows.append(p.coeff_record(float(masses[i])))
+        # Isaac core hands quaternions as wxyz; the reference permutes them at :194
+        self._engine = HydroEngine(n, dtype=self._dtype, device=self._device,
+                                   water_density=first.waterDensity, gravity=first.gravity, quat_order="wxyz")
+        self._engine.set_params_per_body(np.asarray(rows, dtype=np.float64))
+        self._engine.set_articulation(self._bodies_per_robot)
+        dev = self._engine.device
+        self._F = torch.empty(n, 3, dtype=self._dtype, device=dev)
+        self._T = torch.empty(n, 3, dtype=self._dtype, device=dev)
+        self.robot_wrench = (torch.empty(n // self._bodies_per_robot, 6, dtype=self._dtype, device=dev)
+                             if self._bodies_per_robot > 0 else None)
+
+    # ------------------------------------------------------------------ physics step (:138-238)
+    def _on_physics_step(self, delta_time: float):
+        if delta_time <= 1e-6 or self._engine is None or self._view is None or not self._view.is_valid():
+            return
+        self._apply_behavior(delta_time)
+
+    def _apply_behavior(self, delta_time: float):
+        try:
+            positions, orientations = self._view.get_world_poses(clone=False)
+            full_velocities = self._view.get_velocities(clone=False)
+            if full_velocities is None or full_velocities.shape[0] == 0:
+                return
+            dev, dt_ = self._engine.device, self._dtype
+            positions = positions.to(device=dev, dtype=dt_).contiguous()
+            orientations = orientations.to(device=dev, dtype=dt_).contiguous()
+            full_velocities = full_velocities.to(device=dev, dtype=dt_)
+            linear_velocity = full_velocities[:, 0:3].contiguous()
+            angular_velocity = full_velocities[:, 3:6].contiguous()
+        except (UnboundLocalError, IndexError, RuntimeError, AttributeError):
+            return  # the reference silently skips the step (:191-192)
+        self._engine.step(positions, orientations, linear_velocity, angular_velocity, delta_time,
+                          out_force=self._F, out_torque=self._T, out_robot_wrench=self.robot_wrench)
+        self._view.apply_forces_and_torques_at_pos(forces=self._F, torques=self._T, positions=positions,
+                                                   is_global=True)
+
+    def _reset(self):
+        if self._engine is not None:
+            self._engine.close()
+        self._engine = None
+        self._F = self._T = self.robot_wrench = None

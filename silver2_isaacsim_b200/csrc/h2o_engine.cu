@@ -72,6 +72,8 @@ struct h2o_engine {
     bool balance_tiles = false;  // see launch_tile: only pays when the kernel is not issue-bound
     int max_ctas_per_sm = 0;   // 0 = as many as fit
     bool use_pdl = false;      // programmatic dependent launch of the tile kernel
+    int rollout_free_bodies = 0;  // 1: rollouts integrate the bound state between steps (free bodies)
+    double rollout_gravity = 9.81;
     int last_ctas_per_sm = 0;
     // bound tensors
     bool bound = false;
@@ -726,6 +728,58 @@ int h2o_step_bound(h2o_handle h, double dt, h2o_stream stream)
                        e->prev, coeff_at(e, 0), static_cast<cudaStream_t>(stream));
 }
 
+static int integrate_device(h2o_engine* e, void* pos, void* quat, void* lin, void* ang, const void* f,
+                            const void* t, double dt, double gravity, cudaStream_t s)
+{
+    if (e->param_mode < 0) return fail(H2O_ERR_NOT_CONFIGURED, "no parameters set (h2o_set_params_*)");
+    FreeBodyArgs a;
+    memset(&a, 0, sizeof a);
+    a.pos = pos; a.quat = quat; a.lin = lin; a.ang = ang; a.force = f; a.torque = t;
+    a.coeff = e->coeff; a.slot_type = e->slot_type;
+    a.n = e->n; a.n_slots = e->n_slots; a.param_mode = e->param_mode;
+    a.quat_wxyz = e->quat_order == H2O_QUAT_WXYZ;
+    a.dt = dt; a.gravity = gravity;
+    const int grid = int((e->n + 255) / 256);
+    if (e->dtype == H2O_F32) free_body_kernel<float><<<grid, 256, 0, s>>>(a);
+    else free_body_kernel<double><<<grid, 256, 0, s>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    e->launches += 1;
+    return H2O_OK;
+}
+
+int h2o_integrate_free_bodies(h2o_handle h, void* pos, void* quat, void* lin_vel, void* ang_vel, const void* force,
+                              const void* torque, double dt, double gravity, h2o_stream stream)
+{
+    h2o_engine* e = check(h);
+    if (!e) return H2O_ERR_BAD_HANDLE;
+    const void* p[6] = {pos, quat, lin_vel, ang_vel, force, torque};
+    if (int rc = check_ptrs(p, 6)) return rc;
+    if (!(dt > 1e-6)) return H2O_OK;
+    DeviceGuard g(e->device);
+    return integrate_device(e, pos, quat, lin_vel, ang_vel, force, torque, dt, gravity, static_cast<cudaStream_t>(stream));
+}
+
+int h2o_set_rollout_mode(h2o_handle h, int free_bodies, double gravity)
+{
+    h2o_engine* e = check(h);
+    if (!e) return H2O_ERR_BAD_HANDLE;
+    e->rollout_free_bodies = free_bodies != 0;
+    e->rollout_gravity = gravity;
+    return H2O_OK;
+}
+
+// one rollout step over the bound tensors: fused force step (+ free-body integration)
+static int rollout_step(h2o_engine* e, double dt, cudaStream_t s)
+{
+    int rc = step_device(e, e->b_layout, e->b_pos, e->b_quat, e->b_lin, e->b_ang, dt, e->b_f, e->b_t, e->b_w, e->n, 0,
+                         e->prev, coeff_at(e, 0), s);
+    if (rc || !e->rollout_free_bodies) return rc;
+    if (e->b_layout != LAYOUT_SPLIT)
+        return fail(H2O_ERR_NOT_CONFIGURED, "free-body rollouts need the split layout (pos, quat, lin_vel, ang_vel)");
+    return integrate_device(e, const_cast<void*>(e->b_pos), const_cast<void*>(e->b_quat), const_cast<void*>(e->b_lin),
+                            const_cast<void*>(e->b_ang), e->b_f, e->b_t, dt, e->rollout_gravity, s);
+}
+
 int h2o_capture_rollout(h2o_handle h, int n_steps, double dt, h2o_stream stream)
 {
     h2o_engine* e = check(h);
@@ -740,17 +794,14 @@ int h2o_capture_rollout(h2o_handle h, int n_steps, double dt, h2o_stream stream)
     // query happens outside capture.  The capture itself runs on an engine-owned stream: the
     // caller's stream may be the legacy default stream, which cannot be captured.
     const int64_t before0 = e->launches;
-    int rc = step_device(e, e->b_layout, e->b_pos, e->b_quat, e->b_lin, e->b_ang, dt, e->b_f, e->b_t, e->b_w, e->n, 0,
-                         e->prev, coeff_at(e, 0), s);
+    int rc = rollout_step(e, dt, s);
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(s));
     const int64_t per_step = e->launches - before0;
     if (!e->capture_stream) CUDA_TRY(cudaStreamCreateWithFlags(&e->capture_stream, cudaStreamNonBlocking));
     s = e->capture_stream;
     CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    for (int i = 0; i < n_steps && rc == H2O_OK; ++i)
-        rc = step_device(e, e->b_layout, e->b_pos, e->b_quat, e->b_lin, e->b_ang, dt, e->b_f, e->b_t, e->b_w, e->n, 0,
-                         e->prev, coeff_at(e, 0), s);
+    for (int i = 0; i < n_steps && rc == H2O_OK; ++i) rc = rollout_step(e, dt, s);
     cudaGraph_t graph = nullptr;
     cudaError_t err = cudaStreamEndCapture(s, &graph);
     e->launches = before0 + per_step;  // captured launches did not execute

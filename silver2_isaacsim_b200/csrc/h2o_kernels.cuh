@@ -715,4 +715,78 @@ template <typename S> __global__ void unpack_prev_kernel(const S* prev, S* lin, 
     }
 }
 
+// ---------------------------------------------------------------------------
+// free_body_kernel: stand-alone rigid-body stepper for free boxes, so that
+// rollouts (C1 buoy, C5) are self-contained without PhysX.  Semi-implicit Euler: velocities
+// first (hydrodynamic wrench + gravity, box inertia m/12 (b^2 + c^2) in the body frame with the
+// gyroscopic term), then pose with the new velocities; the quaternion is renormalised.
+// Not on the force hot path: arithmetic in double, plain loads/stores, state updated in place.
+// ---------------------------------------------------------------------------
+struct FreeBodyArgs {
+    void *pos, *quat, *lin, *ang;  // (N,3) (N,4) (N,3) (N,3), updated in place
+    const void *force, *torque;    // (N,3) world-frame wrench of this step
+    const void* coeff;             // records (dims + mass) -- per body or part table
+    const int32_t* slot_type;
+    long long n;
+    int n_slots, param_mode, quat_wxyz;
+    double dt, gravity;            // gravity acts along -z
+};
+
+template <typename S> __global__ void __launch_bounds__(256) free_body_kernel(const __grid_constant__ FreeBodyArgs a)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const S* c = reinterpret_cast<const S*>(a.coeff) +
+                 N_COEFF * (a.param_mode == PARAM_PER_BODY ? i : (long long)a.slot_type[i % a.n_slots]);
+    S* P = reinterpret_cast<S*>(a.pos) + 3 * i;
+    S* Q = reinterpret_cast<S*>(a.quat) + 4 * i;
+    S* V = reinterpret_cast<S*>(a.lin) + 3 * i;
+    S* W = reinterpret_cast<S*>(a.ang) + 3 * i;
+    const S* Fp = reinterpret_cast<const S*>(a.force) + 3 * i;
+    const S* Tp = reinterpret_cast<const S*>(a.torque) + 3 * i;
+    const double m = double(c[10]), dx = double(c[0]), dy = double(c[1]), dz = double(c[2]);
+    double qx, qy, qz, qw;
+    if (a.quat_wxyz) { qw = Q[0]; qx = Q[1]; qy = Q[2]; qz = Q[3]; }
+    else { qx = Q[0]; qy = Q[1]; qz = Q[2]; qw = Q[3]; }
+    const double dt = a.dt, im = 1.0 / m;
+    // linear: v += dt (F/m + g)
+    double vx = double(V[0]) + dt * double(Fp[0]) * im;
+    double vy = double(V[1]) + dt * double(Fp[1]) * im;
+    double vz = double(V[2]) + dt * (double(Fp[2]) * im - a.gravity);
+    // angular, body frame: I w' = tau_b - w_b x (I w_b)
+    const double x2 = qx + qx, y2 = qy + qy, z2 = qz + qz;
+    const double r00 = 1 - (qy * y2 + qz * z2), r01 = qx * y2 - qw * z2, r02 = qx * z2 + qw * y2;
+    const double r10 = qx * y2 + qw * z2, r11 = 1 - (qx * x2 + qz * z2), r12 = qy * z2 - qw * x2;
+    const double r20 = qx * z2 - qw * y2, r21 = qy * z2 + qw * x2, r22 = 1 - (qx * x2 + qy * y2);
+    const double Ix = m * (dy * dy + dz * dz) / 12.0, Iy = m * (dx * dx + dz * dz) / 12.0,
+                 Iz = m * (dx * dx + dy * dy) / 12.0;
+    const double tx = double(Tp[0]), ty = double(Tp[1]), tz = double(Tp[2]);
+    const double wx = double(W[0]), wy = double(W[1]), wz = double(W[2]);
+    const double tbx = r00 * tx + r10 * ty + r20 * tz, tby = r01 * tx + r11 * ty + r21 * tz,
+                 tbz = r02 * tx + r12 * ty + r22 * tz;
+    double wbx = r00 * wx + r10 * wy + r20 * wz, wby = r01 * wx + r11 * wy + r21 * wz,
+           wbz = r02 * wx + r12 * wy + r22 * wz;
+    const double gx = wby * (Iz * wbz) - wbz * (Iy * wby), gy = wbz * (Ix * wbx) - wbx * (Iz * wbz),
+                 gz = wbx * (Iy * wby) - wby * (Ix * wbx);
+    wbx += dt * (tbx - gx) / Ix;
+    wby += dt * (tby - gy) / Iy;
+    wbz += dt * (tbz - gz) / Iz;
+    const double nwx = r00 * wbx + r01 * wby + r02 * wbz, nwy = r10 * wbx + r11 * wby + r12 * wbz,
+                 nwz = r20 * wbx + r21 * wby + r22 * wbz;
+    // pose with the NEW velocities; q' = q + dt/2 (0,w) * q
+    const double px = double(P[0]) + dt * vx, py = double(P[1]) + dt * vy, pz = double(P[2]) + dt * vz;
+    const double h = 0.5 * dt;
+    double nqw = qw - h * (nwx * qx + nwy * qy + nwz * qz);
+    double nqx = qx + h * (nwx * qw + nwy * qz - nwz * qy);
+    double nqy = qy + h * (nwy * qw + nwz * qx - nwx * qz);
+    double nqz = qz + h * (nwz * qw + nwx * qy - nwy * qx);
+    const double inv = 1.0 / sqrt(nqx * nqx + nqy * nqy + nqz * nqz + nqw * nqw);
+    nqx *= inv; nqy *= inv; nqz *= inv; nqw *= inv;
+    P[0] = S(px); P[1] = S(py); P[2] = S(pz);
+    V[0] = S(vx); V[1] = S(vy); V[2] = S(vz);
+    W[0] = S(nwx); W[1] = S(nwy); W[2] = S(nwz);
+    if (a.quat_wxyz) { Q[0] = S(nqw); Q[1] = S(nqx); Q[2] = S(nqy); Q[3] = S(nqz); }
+    else { Q[0] = S(nqx); Q[1] = S(nqy); Q[2] = S(nqz); Q[3] = S(nqw); }
+}
+
 }  // namespace h2o

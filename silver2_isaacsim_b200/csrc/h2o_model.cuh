@@ -459,9 +459,12 @@ H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], boo
 {
     // ---- waterline in H (identical to body_terms)
     const H hx2 = in.qx + in.qx, hy2 = in.qy + in.qy, hz2 = in.qz + in.qz;
-    const H r20h = in.qx * hz2 - in.qw * hy2;
-    const H r21h = in.qy * hz2 + in.qw * hx2;
-    const H r22h = H(1) - (in.qx * hx2 + in.qy * hy2);
+    const H hxx = in.qx * hx2, hyy = in.qy * hy2, hzz = in.qz * hz2;
+    const H hxy = in.qx * hy2, hxz = in.qx * hz2, hyz = in.qy * hz2;
+    const H hwx = in.qw * hx2, hwy = in.qw * hy2, hwz = in.qw * hz2;
+    const H r20h = hxz - hwy;
+    const H r21h = hyz + hwx;
+    const H r22h = H(1) - (hxx + hyy);
     const H dqh = ((in.qx * in.qx + in.qy * in.qy) + (in.qz * in.qz + in.qw * in.qw)) - H(1);
     const H dxh = H(in.dimx), dyh = H(in.dimy), dzh = H(in.dimz);
     const H a = r20h * (dxh * H(0.5));
@@ -502,7 +505,6 @@ H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], boo
     ratio_out = ratio;
     const L rl = L(ratio);
     const H fbz = in.rho_h * (ratio * (dxh * dyh * dzh)) * in.grav_h;  // numba_hydrodynamics.py:282
-    const L fb = L(fbz);
 
     // ---- rotation matrix in L (row 2 from the H values)
     const L qx = L(in.qx), qy = L(in.qy), qz = L(in.qz), qw = L(in.qw);
@@ -524,6 +526,22 @@ H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], boo
     const L cbx = L(h2o_popc(mask & KP_XP) - h2o_popc(mask & KP_XN)) * (cinv * hx);
     const L cby = L(h2o_popc(mask & KP_YP) - h2o_popc(mask & KP_YN)) * (cinv * hy);
     const L cbz = L(h2o_popc(mask & KP_ZP) - h2o_popc(mask & KP_ZN)) * (cinv * hz);
+    // Buoyancy torque (cob - p) x (0,0,fb) needs the horizontal offset of the centre of buoyancy,
+    // which vanishes at hydrostatic equilibrium as a difference of O(h) terms: rows 0,1 of R and
+    // the weighted sum are carried in H so that the restoring torque of a floating body keeps
+    // its relative accuracy (a floating buoy sits exactly in that regime).
+    L tbuoy_x, tbuoy_y;
+    {
+        const H sxh = H(h2o_popc(mask & KP_XP) - h2o_popc(mask & KP_XN)) * (dxh * H(0.5));
+        const H syh = H(h2o_popc(mask & KP_YP) - h2o_popc(mask & KP_YN)) * (dyh * H(0.5));
+        const H szh = H(h2o_popc(mask & KP_ZP) - h2o_popc(mask & KP_ZN)) * (dzh * H(0.5));
+        const H cobx_h = (H(1) - (hyy + hzz)) * sxh + (hxy - hwz) * syh + (hxz + hwy) * szh;
+        const H coby_h = (hxy + hwz) * sxh + (H(1) - (hxx + hzz)) * syh + (hyz - hwx) * szh;
+        // the cancellation is over once the sums are formed: scale by fb / count in L
+        const L scale = cinv * L(fbz);
+        tbuoy_x = L(coby_h) * scale;
+        tbuoy_y = -(L(cobx_h) * scale);
+    }
 
     // ---- flow direction, world and body (d = R^T v_hat)
     const L speed2 = in.vx * in.vx + in.vy * in.vy + in.vz * in.vz;
@@ -587,10 +605,10 @@ H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], boo
     const L bby = r01 * in.bx + r11 * in.by + r21 * in.bz;
     const L bbz = r02 * in.bx + r12 * in.by + r22 * in.bz;
 
-    // ---- body-frame torque: cob x (fb R^T z) + psi*(...) + arm x F_l + added inertia
-    const L tbx = psi * tdx + (fb * (cby * r22 - cbz * r21) + ((army * flz - armz * fly) - ma * (d2s + h2s) * bbx));
-    const L tby = psi * tdy + (fb * (cbz * r20 - cbx * r22) + ((armz * flx - armx * flz) - ma * (w2s + h2s) * bby));
-    const L tbz = psi * tdz + (fb * (cbx * r21 - cby * r20) + ((armx * fly - army * flx) - ma * (w2s + d2s) * bbz));
+    // ---- body-frame torque: psi*(...) + arm x F_l + added inertia (buoyancy torque: tbuoy, above)
+    const L tbx = psi * tdx + ((army * flz - armz * fly) - ma * (d2s + h2s) * bbx);
+    const L tby = psi * tdy + ((armz * flx - armx * flz) - ma * (w2s + h2s) * bby);
+    const L tbz = psi * tdz + ((armx * fly - army * flx) - ma * (w2s + d2s) * bbz);
 
     // ---- angular drag (world): -(0.5 rho |w| C V + k min(1, 5|w|)) ratio * w
     const L as2 = in.wx * in.wx + in.wy * in.wy + in.wz * in.wz;
@@ -598,8 +616,8 @@ H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], boo
     const L aq = (as > L(1e-6)) ? L(0.5) * in.rho * as * in.c_drag_ang * vol : L(0);
     const L ka = (aq + in.k_damp_ang * h2o_min(L(1), as * L(5.0))) * rl;
 
-    T[0] = (r00 * tbx + r01 * tby + r02 * tbz) - ka * in.wx;
-    T[1] = (r10 * tbx + r11 * tby + r12 * tbz) - ka * in.wy;
+    T[0] = ((r00 * tbx + r01 * tby + r02 * tbz) - ka * in.wx) + tbuoy_x;
+    T[1] = ((r10 * tbx + r11 * tby + r12 * tbz) - ka * in.wy) + tbuoy_y;
     T[2] = (r20 * tbx + r21 * tby + r22 * tbz) - ka * in.wz;
 
     F[0] = (r00 * flx + r01 * fly + r02 * flz) - (gam * in.vx + ml * in.ax);

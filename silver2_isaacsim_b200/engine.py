@@ -250,6 +250,20 @@ class HydroEngine:
     def step_bound(self, dt: float):
         L.check(self._lib.h2o_step_bound(self._h, float(dt), _stream_ptr(self.device)))
 
+    def set_rollout_mode(self, free_bodies: bool = False, gravity: float = 9.81):
+        """Rollouts over the bound tensors: static state (force-only) or free bodies integrated in place."""
+        L.check(self._lib.h2o_set_rollout_mode(self._h, int(bool(free_bodies)), float(gravity)))
+
+    def integrate_free_bodies(self, position, orientation_quat, linear_vel, angular_vel, force, torque,
+                              dt: float, gravity: float = 9.81):
+        """Harness stepper (semi-implicit Euler, box inertia); updates the four state tensors in place."""
+        for t in (position, orientation_quat, linear_vel, angular_vel, force, torque):
+            if not (t.is_cuda and t.dtype == self.dtype and t.is_contiguous()):
+                raise ValueError("integrate_free_bodies takes contiguous CUDA tensors of the engine dtype")
+        L.check(self._lib.h2o_integrate_free_bodies(
+            self._h, position.data_ptr(), orientation_quat.data_ptr(), linear_vel.data_ptr(), angular_vel.data_ptr(),
+            force.data_ptr(), torque.data_ptr(), float(dt), float(gravity), _stream_ptr(self.device)))
+
     def capture_rollout(self, n_steps: int, dt: float):
         """Capture ``n_steps`` back-to-back steps over the bound tensors into one CUDA graph."""
         L.check(self._lib.h2o_capture_rollout(self._h, int(n_steps), float(dt), _stream_ptr(self.device)))

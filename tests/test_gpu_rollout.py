@@ -1,0 +1,181 @@
+"""BASELINE config 1 (single README buoy, 10 000 steps) and the behaviour adapter, on the GPU."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from silver2_isaacsim_b200 import params as P
+from silver2_isaacsim_b200 import workloads as W
+from tests import scoring
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def buoy_record(oracle):
+    from oracle import free_body
+
+    wl = W.readme_buoy()
+    ctor = P.HydroParams().ctor_row()
+    mass = float(wl.table[0, 10])
+    rec = free_body.rollout(ctor, mass, wl.pos[0], wl.quat_xyzw[0], wl.lin_vel[0], wl.ang_vel[0], wl.dt, 10000)
+    return wl, ctor, mass, rec
+
+
+def test_c1_buoy_settles(buoy_record):
+    """Config 1 feasibility: the 1 m^3 half-density buoy dropped from 1 m settles at its waterline."""
+    wl, ctor, mass, rec = buoy_record
+    assert not rec["raised"].any()  # started dry -> never at rest while wet
+    z = rec["pos"][:, 2]
+    assert z[0] == 1.0 and abs(z[-1]) < 5e-3 and np.abs(rec["v"][-1]).max() < 2e-2
+    assert np.abs(rec["F"]).max() <= 500 * mass * (1 + 1e-12)  # clamp bound
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["fp32", "fp64"])
+def test_c1_teacher_forced_10k_steps(buoy_record, dev, dtype):
+    """Replay the oracle's 10 000-state sequence through the CUDA step (one body per time step,
+    previous velocities = the behaviour's carried state) and compare F, tau step by step."""
+    from silver2_isaacsim_b200 import HydroEngine
+
+    wl, ctor, mass, rec = buoy_record
+    n = len(rec["pos"])
+    e = HydroEngine(n, dtype=dtype, device=dev)
+    e.set_params_uniform(ctor, mass)
+    if dtype == torch.float32:
+        # feed fp32-representable states to both sides
+        cast = lambda a: a.astype(np.float32).astype(np.float64)
+        from oracle import hydro_oracle as O
+        ref = O.step(np.array(ctor, float), [mass], cast(rec["pos"]), cast(rec["quat"]), cast(rec["v"]), cast(rec["w"]),
+                     cast(rec["prev_v"]), cast(rec["prev_w"]), wl.dt)
+        Fr, Tr = ref.force, ref.torque
+    else:
+        cast = lambda a: a
+        Fr, Tr = rec["F"], rec["T"]
+    t = lambda a: torch.as_tensor(cast(a), device=dev).to(dtype).contiguous()
+    e.set_prev(t(rec["prev_v"]), t(rec["prev_w"]))
+    F, T = e.step(t(rec["pos"]), t(rec["quat"]), t(rec["v"]), t(rec["w"]), wl.dt)
+    F, T = F.double().cpu().numpy(), T.double().cpu().numpy()
+    if dtype == torch.float32:
+        scoring.assert_fp32(F, Fr, "C1 force", min_pass=0.999)
+        scoring.assert_fp32(T, Tr, "C1 torque", min_pass=0.999)
+    else:
+        scale = np.full(n, 1025.0 * 9.81)
+        assert scoring.fp64_ok(F, Fr, scale).all()
+        assert scoring.fp64_ok(T, Tr, scale).all()  # |p_xy| ~ 0: the strict torque criterion applies
+
+
+def test_c1_free_running_graph_rollout(buoy_record, dev):
+    """10 000 steps on the device (fused step + free-body stepper, 100 replays of a captured
+    100-step CUDA graph) against the float64 NumPy rollout.
+
+    The model is discontinuous (a keypoint crossing the surface moves the centre of buoyancy by a
+    finite amount), so the rollout is chaotic: perturbing the NumPy rollout's initial height by
+    1e-15 moves it by 5e-9 after 500 steps and 3e-4 after 1000.  Hence: tight agreement while
+    rounding noise has not been amplified yet, same settled state at the end, drift reported."""
+    from silver2_isaacsim_b200 import HydroEngine
+
+    wl, ctor, mass, rec = buoy_record
+    e = HydroEngine(1, dtype=torch.float64, device=dev)
+    e.set_params_uniform(ctor, mass)
+    t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64), device=dev).contiguous()
+    pos, quat, v, w = t(wl.pos), t(wl.quat_xyzw), t(wl.lin_vel), t(wl.ang_vel)
+    F, T = e.bind(pos, quat, v, w)
+    e.set_rollout_mode(free_bodies=True, gravity=wl.g)
+    e.capture_rollout(99, wl.dt)        # capture itself advances one eager step
+    drift = {}
+    for k in range(100):
+        if k:
+            e.step_bound(wl.dt)         # the eager step that capture did in round 0
+            e.integrate_free_bodies(pos, quat, v, w, F, T, wl.dt, wl.g)
+        e.launch_rollout()
+        n_done = 100 * (k + 1)
+        if n_done in (100, 200, 500, 1000, 5000):
+            torch.cuda.synchronize()
+            drift[n_done] = float(np.abs(pos.cpu().numpy()[0] - rec["pos"][n_done]).max())
+    torch.cuda.synchronize()
+    pf, qf, vf, wf = rec["final"]
+    drift[10000] = float(np.abs(pos.cpu().numpy()[0] - pf).max())
+    print("free-running drift |p_gpu - p_numpy|:", {k: "%.2e" % d for k, d in drift.items()})
+    assert e.launch_count == 20000      # (fused step + stepper) x 10 000, 19 800 of them graph nodes
+    assert drift[100] < 1e-11 and drift[200] < 1e-9, drift
+    assert max(drift.values()) < 2e-2, drift
+    assert np.abs(v.cpu().numpy()[0] - vf).max() < 2e-2
+    assert abs(pos.cpu().numpy()[0][2] - pf[2]) < 5e-3 and abs(pf[2]) < 5e-3  # same waterline
+
+
+class FakeRigidPrimView:
+    """Stand-in for omni.isaac.core.prims.RigidPrimView (the three methods the reference uses)."""
+
+    def __init__(self, pos, quat_wxyz, vel, masses):
+        self.pos, self.quat, self.vel, self.masses = pos, quat_wxyz, vel, masses
+        self.applied = None
+        self.valid = True
+
+    def is_valid(self):
+        return self.valid
+
+    def get_world_poses(self, clone=False):
+        return self.pos, self.quat
+
+    def get_velocities(self, clone=False):
+        return self.vel
+
+    def get_masses(self, clone=False):
+        return self.masses
+
+    def apply_forces_and_torques_at_pos(self, forces, torques, positions, is_global):
+        assert is_global
+        self.applied = (forces.clone(), torques.clone(), positions.clone())
+
+
+def test_batched_behavior_adapter(oracle, dev):
+    """f1: one behaviour for the 19 SILVER2 prims + the buoy, JSON name matching, wxyz input,
+    two physics steps (v_prev = 0 then v_prev = v), reset on stop."""
+    from silver2_isaacsim_b200.behavior import BatchedHydrodynamicsBehavior
+
+    names = list(P.HEXAPOD_SLOTS) + ["Obsea_Buoy"]
+    rng = np.random.default_rng(7)
+    n = len(names)
+    pos = np.concatenate([rng.uniform(-0.4, 0.4, (19, 3)) + [2, 10.7, -0.2], [[5.0, 5.0, -0.3]]]).astype(np.float32)
+    q = rng.normal(size=(n, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True); q = q.astype(np.float32)
+    vel = rng.normal(size=(n, 6)).astype(np.float32) * 0.3
+    cfg = P.load_config()
+    masses = np.array([cfg["masses"].get(P.match_part(nm, cfg) or "", 512.5) for nm in names], dtype=np.float32)
+    tt = lambda a: torch.as_tensor(a, device=dev)
+    view = FakeRigidPrimView(tt(pos), tt(q[:, [3, 0, 1, 2]].copy()), tt(vel), tt(masses))
+    b = BatchedHydrodynamicsBehavior(names, view, device="cuda:0")
+    assert b.part_of[0] == "body" and b.part_of[1] == "coxa" and b.part_of[-1] is None
+    assert b.exposed["Obsea_Buoy"].xDimension == 1.0 and b.exposed["Tibia_5"].linearDamping == 20.0
+    b._on_physics_step(1 / 60)          # not playing yet: nothing happens (engine is None)
+    assert view.applied is None
+    b.on_play()
+    b._on_physics_step(1e-7)            # dt guard (:139)
+    assert view.applied is None
+    dt = 1 / 60
+    ctor = np.array([b.exposed[nm].ctor_row() for nm in names])
+    zero = np.zeros((n, 3))
+    for prev_v, prev_w in ((zero, zero), (vel[:, :3], vel[:, 3:])):
+        b._on_physics_step(dt)
+        ref = oracle.step(ctor, masses, pos, q, vel[:, :3], vel[:, 3:], prev_v, prev_w, dt)
+        F, T, Ppos = view.applied
+        scoring.assert_fp32(F.cpu().numpy(), ref.force, "behaviour force", min_pass=1.0)
+        scoring.assert_fp32(T.cpu().numpy(), ref.torque, "behaviour torque", min_pass=1.0)
+        assert torch.equal(Ppos, view.pos)
+    view.valid = False
+    view.applied = None
+    b._on_physics_step(dt)              # invalid view: skipped (:139)
+    assert view.applied is None
+    b.on_stop()
+    assert b._engine is None
+    view.valid = True
+    b.on_play()                         # play again: carried velocities start from zero (:240-245)
+    b._on_physics_step(dt)
+    ref = oracle.step(ctor, masses, pos, q, vel[:, :3], vel[:, 3:], zero, zero, dt)
+    scoring.assert_fp32(view.applied[0].cpu().numpy(), ref.force, "after reset", min_pass=1.0)

@@ -20,7 +20,7 @@ def _ref(oracle, wl):
 def test_fp32_mode_policy(oracle, make):
     wl = make()
     ref = _ref(oracle, wl)
-    F, T, _, _ = emul.step(wl, emul.MODE_FP32)
+    F, T, _, _ = emul.step(wl, emul.MODE_FP32_FAST)  # what the fused fp32 step kernels run
     scoring.assert_fp32(F, ref.force, f"{wl.name} force")
     scoring.assert_fp32(T, ref.torque, f"{wl.name} torque")
 
