@@ -52,8 +52,10 @@ struct StepArgs {
     double* stats;           // N_STATS doubles or nullptr
     long long n;             // bodies
     long long first_body;    // global index of body 0 of this launch (slot lookup)
-    int tile_bodies;         // bodies per tile (multiple of 4 and of bodies_per_robot)
-    int n_tiles;             // number of FULL tiles handled by the TMA path
+    int tile_bodies;         // largest tile in bodies (multiple of `unit`, <= threads per CTA)
+    int unit;                // tile granule: 16-byte element granule, whole robots if articulated
+    long long n_units;       // granules available to the tile kernel
+    int split_remainder;     // 1: split the last, incomplete round evenly over all CTAs (partial tiles)
     int n_slots, n_types;
     int bodies_per_robot;    // 0 = no articulation
     int quat_wxyz;           // 1: incoming quaternions are wxyz (Isaac core), else xyzw
@@ -321,6 +323,7 @@ template <typename S, int kLayout, int kParam> struct TileLayout {
     static constexpr int E_COEFF = (kParam == PARAM_PER_BODY) ? N_COEFF : 0;
     static constexpr int E_IN = E_POS + E_QUAT + E_LIN + E_ANG + E_PREV + E_COEFF;
     static constexpr int E_OUT = 3 + 3 + 6;  // force, torque, prev
+    static constexpr int E_IN_ALL = E_IN;
 };
 
 template <typename S, int kLayout, int kParam, int kThreads, int kStagesIn, int kStagesOut>
@@ -373,12 +376,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
     const uint32_t b_lin = uint32_t(TL::E_LIN) * TB * sizeof(S);
     const uint32_t b_ang = uint32_t(TL::E_ANG) * TB * sizeof(S);
     const uint32_t b_prev = uint32_t(TL::E_PREV) * TB * sizeof(S);
-    const uint32_t b_coeff = uint32_t(TL::E_COEFF) * TB * sizeof(S);
+    // stage layout is fixed by the largest tile; partial tiles just copy fewer bytes per stream
     const uint32_t o_quat = b_pos, o_lin = o_quat + b_quat, o_ang = o_lin + b_lin, o_prev = o_ang + b_ang,
                    o_coeff = o_prev + b_prev;
-    const uint32_t bytes_in = o_coeff + b_coeff;
-    const uint32_t b_f = 3u * TB * sizeof(S);
-    const uint32_t oo_t = b_f, oo_prev = 2 * b_f;
+    const uint32_t oo_t = 3u * TB * sizeof(S), oo_prev = 2 * oo_t;
 
     pdl_launch_dependents();  // no-op unless launched with the PDL attribute
     if (tid == 0) {
@@ -394,41 +395,66 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
     }
     __syncthreads();
 
-    auto issue_loads = [&](int tile, int stage) {
+    // Tile schedule.  Full rounds are dealt round-robin (tile = round*grid + cta): at any moment the
+    // resident CTAs stream one compact window of every array, which is what DRAM pages and the TLB
+    // like (one contiguous share per CTA instead costs ~10 % of the bandwidth).  The bodies that do
+    // not fill a whole round are split evenly over ALL CTAs as one last, partial tile each, so every
+    // CTA finishes together and the final (drain) wave is short.
+    const long long tileable = a.n_units * a.unit;
+    const long long n_tiles_full = tileable / TB;
+    const int n_full = int(tileable / ((long long)TB * gridDim.x));
+    const long long rest0 = (long long)n_full * gridDim.x * TB;
+    long long ru0 = 0;
+    int last_cnt = 0;
+    if (a.split_remainder) {
+        const long long rest_units = (tileable - rest0) / a.unit;
+        ru0 = (long long)blockIdx.x * rest_units / gridDim.x;
+        const long long ru1 = (long long)(blockIdx.x + 1) * rest_units / gridDim.x;
+        last_cnt = int((ru1 - ru0) * a.unit);
+    } else if ((long long)n_full * gridDim.x + blockIdx.x < n_tiles_full) {
+        // plain round-robin: the ragged last round is taken by the first CTAs as full tiles
+        ru0 = (long long)blockIdx.x * (TB / a.unit);
+        last_cnt = TB;
+    }
+    const int n_it = n_full + (last_cnt > 0 ? 1 : 0);
+    auto tile_count = [&](int it) -> int { return it < n_full ? TB : last_cnt; };
+    auto tile_start = [&](int it) -> long long {
+        return it < n_full ? ((long long)it * gridDim.x + blockIdx.x) * TB : rest0 + ru0 * a.unit;
+    };
+    auto issue_loads = [&](int it, int stage) {
         unsigned char* dst = smem + SM::OFF_IN + size_t(stage) * SM::IN_BYTES;
-        const long long b0 = (long long)tile * TB;
+        const long long b0 = tile_start(it);
+        const uint32_t cb = uint32_t(tile_count(it)) * sizeof(S);  // bytes per body-scalar column
         uint64_t* bar = &full_bar[stage];
-        mbar_arrive_expect_tx(bar, bytes_in);
-        bulk_g2s(dst, reinterpret_cast<const S*>(a.pos) + b0 * TL::E_POS, b_pos, bar);
-        if (TL::E_QUAT) bulk_g2s(dst + o_quat, reinterpret_cast<const S*>(a.quat) + b0 * TL::E_QUAT, b_quat, bar);
-        bulk_g2s(dst + o_lin, reinterpret_cast<const S*>(a.lin) + b0 * TL::E_LIN, b_lin, bar);
-        if (TL::E_ANG) bulk_g2s(dst + o_ang, reinterpret_cast<const S*>(a.ang) + b0 * TL::E_ANG, b_ang, bar);
-        bulk_g2s(dst + o_prev, reinterpret_cast<const S*>(a.prev) + b0 * TL::E_PREV, b_prev, bar);
+        mbar_arrive_expect_tx(bar, cb * TL::E_IN);
+        bulk_g2s(dst, reinterpret_cast<const S*>(a.pos) + b0 * TL::E_POS, cb * TL::E_POS, bar);
+        if (TL::E_QUAT) bulk_g2s(dst + o_quat, reinterpret_cast<const S*>(a.quat) + b0 * TL::E_QUAT, cb * TL::E_QUAT, bar);
+        bulk_g2s(dst + o_lin, reinterpret_cast<const S*>(a.lin) + b0 * TL::E_LIN, cb * TL::E_LIN, bar);
+        if (TL::E_ANG) bulk_g2s(dst + o_ang, reinterpret_cast<const S*>(a.ang) + b0 * TL::E_ANG, cb * TL::E_ANG, bar);
+        bulk_g2s(dst + o_prev, reinterpret_cast<const S*>(a.prev) + b0 * TL::E_PREV, cb * TL::E_PREV, bar);
         if (TL::E_COEFF)
-            bulk_g2s(dst + o_coeff, reinterpret_cast<const S*>(a.coeff) + b0 * TL::E_COEFF, b_coeff, bar);
+            bulk_g2s(dst + o_coeff, reinterpret_cast<const S*>(a.coeff) + b0 * TL::E_COEFF, cb * TL::E_COEFF, bar);
     };
 
-    const int first = blockIdx.x, stride = gridDim.x;
     if (tid == 0) {  // prologue: arm every input stage
-        for (int j = 0; j < kStagesIn; ++j) {
-            const int tile = first + j * stride;
-            if (tile < a.n_tiles) issue_loads(tile, j);
-        }
+        for (int j = 0; j < kStagesIn; ++j)
+            if (j < n_it) issue_loads(j, j);
     }
 
     ThreadStats st;
     const S inv_dt = S(a.inv_dt);
     const int bpr = a.bodies_per_robot;
-    const int robots_per_tile = kRobot ? TB / bpr : 0;
-    const bool active = tid < TB;
 
-    int it = 0;
-    for (int tile = first; tile < a.n_tiles; tile += stride, ++it) {
+    for (int it = 0; it < n_it; ++it) {
         const int stage = it % kStagesIn;
         const int ostage = it % kStagesOut;
+        const int cnt = tile_count(it);
+        const long long tile_begin = tile_start(it);
+        const bool active = tid < cnt;
+        const int robots_in_tile = kRobot ? cnt / bpr : 0;
         if (kRobot) {
             // same thread <-> same index as the read-out loop below: no barrier needed in between
-            for (int i = tid; i < robots_per_tile * 6; i += kThreads) robot_acc[i] = 0.0;
+            for (int i = tid; i < robots_in_tile * 6; i += kThreads) robot_acc[i] = 0.0;
         }
         mbar_wait(&full_bar[stage], (it / kStagesIn) & 1);
 
@@ -453,7 +479,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
             } else {
                 int slot = 0;
                 if (a.n_slots > 1) {
-                    const int base_mod = int((a.first_body + (long long)tile * TB) % a.n_slots);
+                    const int base_mod = int((a.first_body + tile_begin) % a.n_slots);
                     slot = (base_mod + tid) % a.n_slots;
                 }
                 c = table + N_COEFF * int(slot_map[slot]);
@@ -469,16 +495,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
         // the bulk store that last used this output stage must have finished reading it
         if (tid == 0) bulk_wait_read<kStagesOut - 1>();
         __syncthreads();  // (A) input stage consumed, output stage free
-        if (tid == 0) {
-            const int nxt = tile + kStagesIn * stride;
-            if (nxt < a.n_tiles) issue_loads(nxt, stage);
-        }
+        if (tid == 0 && it + kStagesIn < n_it) issue_loads(it + kStagesIn, stage);
 
         S F[3] = {S(0), S(0), S(0)}, T[3] = {S(0), S(0), S(0)};
         unsigned char* out = smem + SM::OFF_OUT + size_t(ostage) * SM::OUT_BYTES;
         if (active) {
             if (kCopyOnly) {
-                // measurement aid (tile config 10): same memory traffic, no arithmetic
+                // measurement aid (tile configs 10/11): same memory traffic, no arithmetic
                 F[0] = r.px + cl[0]; F[1] = r.py + cl[3]; F[2] = r.pz + cl[6];
                 T[0] = r.q0 + cl[9]; T[1] = r.q1 + r.q2 + r.pvx + r.pvz; T[2] = r.q3 + cl[10] + r.pwy;
             } else {
@@ -516,15 +539,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
         __syncthreads();  // (C) results (and robot accumulators) complete
 
         if (tid == 0) {
-            const long long b0 = (long long)tile * TB;
-            bulk_s2g(reinterpret_cast<S*>(a.out_force) + b0 * 3, out, b_f);
-            bulk_s2g(reinterpret_cast<S*>(a.out_torque) + b0 * 3, out + oo_t, b_f);
-            bulk_s2g(reinterpret_cast<S*>(a.prev) + b0 * 6, out + oo_prev, b_prev);
+            const uint32_t cb = uint32_t(cnt) * sizeof(S);
+            bulk_s2g(reinterpret_cast<S*>(a.out_force) + tile_begin * 3, out, cb * 3);
+            bulk_s2g(reinterpret_cast<S*>(a.out_torque) + tile_begin * 3, out + oo_t, cb * 3);
+            bulk_s2g(reinterpret_cast<S*>(a.prev) + tile_begin * 6, out + oo_prev, cb * 6);
             bulk_commit();
         }
         if (kRobot) {
-            S* ow = reinterpret_cast<S*>(a.out_wrench) + ((long long)tile * robots_per_tile) * 6;
-            for (int i = tid; i < robots_per_tile * 6; i += kThreads) ow[i] = S(robot_acc[i]);
+            S* ow = reinterpret_cast<S*>(a.out_wrench) + (tile_begin / bpr) * 6;
+            for (int i = tid; i < robots_in_tile * 6; i += kThreads) ow[i] = S(robot_acc[i]);
         }
     }
     if (tid == 0) bulk_wait_all<0>();
