@@ -70,7 +70,6 @@ struct h2o_engine {
     int sm_count = 148;
     int tile_cfg = 0;          // 0 = default configuration of the dtype
     int max_ctas_per_sm = 0;   // 0 = as many as fit
-    int split_remainder = 0;   // tile schedule of the last, incomplete round (see step_tile_kernel)
     bool use_pdl = false;      // programmatic dependent launch of the tile kernel
     int rollout_free_bodies = 0;  // 1: rollouts integrate the bound state between steps (free bodies)
     double rollout_gravity = 9.81;
@@ -179,21 +178,13 @@ static int launch_tile(h2o_engine* e, StepArgs& a, cudaStream_t stream)
         if (c < 1) return fail(H2O_ERR_CUDA, "tile kernel does not fit on an SM (smem %zu)", TLn::smem());
         ctas_per_sm[dev] = c;
     }
-    // Full rounds of tile_bodies-sized tiles are dealt round-robin over the resident CTAs; the
-    // bodies that do not fill a round are split evenly (in granules of `unit` bodies: the 16-byte
-    // element granule, whole robots when articulated) as one partial tile per CTA -- see the
-    // kernel.  A ragged last round (8192 tiles over 888 CTAs = 9.2 rounds) is avoided.
     const int tb_max = tile_bodies_for(C::kThreads, sizeof(S), kRobot ? a.bodies_per_robot : 0);
     int cps = ctas_per_sm[dev];
     if (e->max_ctas_per_sm > 0) cps = std::min(cps, e->max_ctas_per_sm);
     const long long slots = (long long)e->sm_count * cps;
     a.tile_bodies = tb_max;
-    a.unit = int(tile_unit(sizeof(S), kRobot ? a.bodies_per_robot : 0));
-    a.n_units = a.n / a.unit;
-    a.split_remainder = e->split_remainder;
-    if (!a.split_remainder) a.n_units = (a.n / tb_max) * (tb_max / a.unit);  // full tiles only
-    const long long tiles_needed = (a.n_units * a.unit + tb_max - 1) / tb_max;
-    const int grid = int(std::max<long long>(1, std::min<long long>(tiles_needed, slots)));
+    a.n_tiles = int(std::min<long long>(a.n / tb_max, 0x7fffffff));
+    const int grid = int(std::max<long long>(1, std::min<long long>(a.n_tiles, slots)));
     if (e->use_pdl) {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof cfg);
@@ -288,7 +279,7 @@ static int step_typed2(h2o_engine* e, StepArgs& a, cudaStream_t stream)
                         : launch_tile<S, kLayout, kParam, false, kStats, DC>(e, a, stream);
         }
         if (rc) return rc;
-        done_bodies = a.n_units * a.unit;
+        done_bodies = (long long)a.n_tiles * a.tile_bodies;
         e->last_kernel = H2O_KERNEL_TILE;
     } else {
         e->last_kernel = H2O_KERNEL_DIRECT;
@@ -403,7 +394,6 @@ int h2o_create(h2o_handle* out, int64_t n_bodies, int dtype, int device)
     e->sm_count = prop.multiProcessorCount;
     if (const char* v = getenv("H2O_MAX_CTAS_PER_SM")) e->max_ctas_per_sm = atoi(v);
     if (const char* v = getenv("H2O_PDL")) e->use_pdl = atoi(v) != 0;
-    if (const char* v = getenv("H2O_SPLIT_REMAINDER")) e->split_remainder = atoi(v);
     if (cudaMalloc(&e->prev, size_t(n_bodies) * 6 * e->esz) != cudaSuccess ||
         cudaMalloc(reinterpret_cast<void**>(&e->stats), N_STATS * sizeof(double)) != cudaSuccess) {
         cudaGetLastError();

@@ -53,9 +53,7 @@ struct StepArgs {
     long long n;             // bodies
     long long first_body;    // global index of body 0 of this launch (slot lookup)
     int tile_bodies;         // largest tile in bodies (multiple of `unit`, <= threads per CTA)
-    int unit;                // tile granule: 16-byte element granule, whole robots if articulated
-    long long n_units;       // granules available to the tile kernel
-    int split_remainder;     // 1: split the last, incomplete round evenly over all CTAs (partial tiles)
+    int n_tiles;             // number of full tiles handled by the tile kernel (the rest: direct kernel)
     int n_slots, n_types;
     int bodies_per_robot;    // 0 = no articulation
     int quat_wxyz;           // 1: incoming quaternions are wxyz (Isaac core), else xyzw
@@ -201,8 +199,15 @@ __device__ __forceinline__ void make_body_in(const RawBody<S>& r, const S* c, in
     }
     in.vx = r.vx; in.vy = r.vy; in.vz = r.vz;
     in.wx = r.wx; in.wy = r.wy; in.wz = r.wz;
-    in.ax = (r.vx - r.pvx) * inv_dt; in.ay = (r.vy - r.pvy) * inv_dt; in.az = (r.vz - r.pvz) * inv_dt;
-    in.bx = (r.wx - r.pwx) * inv_dt; in.by = (r.wy - r.pwy) * inv_dt; in.bz = (r.wz - r.pwz) * inv_dt;
+    if (sizeof(S) == 4) {  // fp32 fast path folds 1/dt into the added-mass constants
+        in.ax = r.vx - r.pvx; in.ay = r.vy - r.pvy; in.az = r.vz - r.pvz;
+        in.bx = r.wx - r.pwx; in.by = r.wy - r.pwy; in.bz = r.wz - r.pwz;
+        in.acc_scale = inv_dt;
+    } else {
+        in.ax = (r.vx - r.pvx) * inv_dt; in.ay = (r.vy - r.pvy) * inv_dt; in.az = (r.vz - r.pvz) * inv_dt;
+        in.bx = (r.wx - r.pwx) * inv_dt; in.by = (r.wy - r.pwy) * inv_dt; in.bz = (r.wz - r.pwz) * inv_dt;
+        in.acc_scale = S(1);
+    }
     in.dimx = c[0]; in.dimy = c[1]; in.dimz = c[2];
     in.c_drag = c[3]; in.c_drag_ang = c[4]; in.k_damp = c[5]; in.k_damp_ang = c[6];
     in.c_am = c[7]; in.c_am_ang = c[8]; in.c_lift = c[9];
@@ -395,36 +400,18 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
     }
     __syncthreads();
 
-    // Tile schedule.  Full rounds are dealt round-robin (tile = round*grid + cta): at any moment the
-    // resident CTAs stream one compact window of every array, which is what DRAM pages and the TLB
-    // like (one contiguous share per CTA instead costs ~10 % of the bandwidth).  The bodies that do
-    // not fill a whole round are split evenly over ALL CTAs as one last, partial tile each, so every
-    // CTA finishes together and the final (drain) wave is short.
-    const long long tileable = a.n_units * a.unit;
-    const long long n_tiles_full = tileable / TB;
-    const int n_full = int(tileable / ((long long)TB * gridDim.x));
-    const long long rest0 = (long long)n_full * gridDim.x * TB;
-    long long ru0 = 0;
-    int last_cnt = 0;
-    if (a.split_remainder) {
-        const long long rest_units = (tileable - rest0) / a.unit;
-        ru0 = (long long)blockIdx.x * rest_units / gridDim.x;
-        const long long ru1 = (long long)(blockIdx.x + 1) * rest_units / gridDim.x;
-        last_cnt = int((ru1 - ru0) * a.unit);
-    } else if ((long long)n_full * gridDim.x + blockIdx.x < n_tiles_full) {
-        // plain round-robin: the ragged last round is taken by the first CTAs as full tiles
-        ru0 = (long long)blockIdx.x * (TB / a.unit);
-        last_cnt = TB;
-    }
-    const int n_it = n_full + (last_cnt > 0 ? 1 : 0);
-    auto tile_count = [&](int it) -> int { return it < n_full ? TB : last_cnt; };
-    auto tile_start = [&](int it) -> long long {
-        return it < n_full ? ((long long)it * gridDim.x + blockIdx.x) * TB : rest0 + ru0 * a.unit;
-    };
+    // Tile schedule: full tiles dealt round-robin (tile = cta + it*grid).  At any moment the resident
+    // CTAs stream one compact window of every array, which is what DRAM pages and the TLB like.
+    // Measured alternatives (profiles/r01_sweep_schedules.log): one contiguous share per CTA costs
+    // ~10 % of the bandwidth; splitting the ragged last round evenly over all CTAs is ~0.8 us slower.
+    const int n_it = (a.n_tiles > int(blockIdx.x)) ? (a.n_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
+    const long long round_stride = (long long)gridDim.x * TB;
+    const long long first_begin = (long long)blockIdx.x * TB;
+    auto tile_start = [&](int it) -> long long { return first_begin + it * round_stride; };
     auto issue_loads = [&](int it, int stage) {
         unsigned char* dst = smem + SM::OFF_IN + size_t(stage) * SM::IN_BYTES;
         const long long b0 = tile_start(it);
-        const uint32_t cb = uint32_t(tile_count(it)) * sizeof(S);  // bytes per body-scalar column
+        const uint32_t cb = uint32_t(TB) * sizeof(S);  // bytes per body-scalar column
         uint64_t* bar = &full_bar[stage];
         mbar_arrive_expect_tx(bar, cb * TL::E_IN);
         bulk_g2s(dst, reinterpret_cast<const S*>(a.pos) + b0 * TL::E_POS, cb * TL::E_POS, bar);
@@ -445,11 +432,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
     const S inv_dt = S(a.inv_dt);
     const int bpr = a.bodies_per_robot;
 
+    long long next_begin = first_begin;
     for (int it = 0; it < n_it; ++it) {
         const int stage = it % kStagesIn;
         const int ostage = it % kStagesOut;
-        const int cnt = tile_count(it);
-        const long long tile_begin = tile_start(it);
+        const int cnt = TB;
+        const long long tile_begin = next_begin;
+        next_begin += round_stride;
         const bool active = tid < cnt;
         const int robots_in_tile = kRobot ? cnt / bpr : 0;
         if (kRobot) {
@@ -687,6 +676,7 @@ __global__ void __launch_bounds__(256) components_kernel(const __grid_constant__
     make_body_in<S>(r, c, a.quat_wxyz, a.rho, a.grav, S(0), in);
     in.ax = la[0]; in.ay = la[1]; in.az = la[2];
     in.bx = aa[0]; in.by = aa[1]; in.bz = aa[2];
+    in.acc_scale = S(1);
     Terms<double, S> t;
     body_terms<double, S, false>(in, t);
     const bool wet = t.ratio > 0.0;

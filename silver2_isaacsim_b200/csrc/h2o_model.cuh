@@ -169,8 +169,10 @@ template <typename H, typename L> struct BodyIn {
     H qx, qy, qz, qw;     // orientation, xyzw
     L vx, vy, vz;         // linear velocity (world)
     L wx, wy, wz;         // angular velocity (world)
-    L ax, ay, az;         // linear acceleration (world)
-    L bx, by, bz;         // angular acceleration (world)
+    L ax, ay, az;         // linear acceleration (world) ...
+    L bx, by, bz;         // angular acceleration (world) ...
+    L acc_scale;          // ... both to be multiplied by this (1, or 1/dt when a,b hold velocity differences;
+                          //     only body_wrench_fast honours it, folding it into the added-mass constants)
     // coefficient record (params.py COEFF_FIELDS) + globals
     L dimx, dimy, dimz;
     L c_drag, c_drag_ang, k_damp, k_damp_ang, c_am, c_am_ang, c_lift;
@@ -516,16 +518,16 @@ H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], boo
     const L r20 = L(r20h), r21 = L(r21h), r22 = L(r22h);
     const L k4 = L(4) * L(dqh);
 
-    const L hx = in.dimx * L(0.5), hy = in.dimy * L(0.5), hz = in.dimz * L(0.5);
     const L ayz = in.dimy * in.dimz, axz = in.dimx * in.dimz, axy = in.dimx * in.dimy;
     const L vol = in.dimx * ayz;
 
     // ---- centre of buoyancy in the body frame: h .* sum(sign)/count
     const int cnt = h2o_popc(mask);
     const L cinv = (partial && cnt > 0) ? h2o_rcp(L(cnt)) : L(0);
-    const L cbx = L(h2o_popc(mask & KP_XP) - h2o_popc(mask & KP_XN)) * (cinv * hx);
-    const L cby = L(h2o_popc(mask & KP_YP) - h2o_popc(mask & KP_YN)) * (cinv * hy);
-    const L cbz = L(h2o_popc(mask & KP_ZP) - h2o_popc(mask & KP_ZN)) * (cinv * hz);
+    const L chalf = cinv * L(0.5);
+    const L cbx = L(h2o_popc(mask & KP_XP) - h2o_popc(mask & KP_XN)) * (chalf * in.dimx);
+    const L cby = L(h2o_popc(mask & KP_YP) - h2o_popc(mask & KP_YN)) * (chalf * in.dimy);
+    const L cbz = L(h2o_popc(mask & KP_ZP) - h2o_popc(mask & KP_ZN)) * (chalf * in.dimz);
     // Buoyancy torque (cob - p) x (0,0,fb) needs the horizontal offset of the centre of buoyancy,
     // which vanishes at hydrostatic equilibrium as a difference of O(h) terms: rows 0,1 of R and
     // the weighted sum are carried in H so that the restoring torque of a floating body keeps
@@ -597,7 +599,7 @@ H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], boo
     const L flx = -(d0 * tl), fly = -(d1 * tl), flz = an2 * sl;  // body frame
 
     // ---- added mass: force in the world frame, inertia torque in the body frame
-    const L rv = vol * in.rho * rl;
+    const L rv = vol * in.rho * rl * in.acc_scale;
     const L ml = rv * in.c_am;
     const L ma = rv * in.c_am_ang;
     const L w2s = in.dimx * in.dimx, d2s = in.dimy * in.dimy, h2s = in.dimz * in.dimz;

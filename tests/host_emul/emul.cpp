@@ -26,12 +26,14 @@ static void run(int64_t n, const double* pos, const double* quat, const double* 
         const L wx = L(S(w[3 * i])), wy = L(S(w[3 * i + 1])), wz = L(S(w[3 * i + 2]));
         in.vx = vx; in.vy = vy; in.vz = vz;
         in.wx = wx; in.wy = wy; in.wz = wz;
-        in.ax = (vx - L(S(pl[3 * i]))) * inv_dt;
-        in.ay = (vy - L(S(pl[3 * i + 1]))) * inv_dt;
-        in.az = (vz - L(S(pl[3 * i + 2]))) * inv_dt;
-        in.bx = (wx - L(S(pa[3 * i]))) * inv_dt;
-        in.by = (wy - L(S(pa[3 * i + 1]))) * inv_dt;
-        in.bz = (wz - L(S(pa[3 * i + 2]))) * inv_dt;
+        const L sc = kFast ? L(1) : inv_dt;  // the fast path folds 1/dt into the added-mass constants
+        in.acc_scale = kFast ? inv_dt : L(1);
+        in.ax = (vx - L(S(pl[3 * i]))) * sc;
+        in.ay = (vy - L(S(pl[3 * i + 1]))) * sc;
+        in.az = (vz - L(S(pl[3 * i + 2]))) * sc;
+        in.bx = (wx - L(S(pa[3 * i]))) * sc;
+        in.by = (wy - L(S(pa[3 * i + 1]))) * sc;
+        in.bz = (wz - L(S(pa[3 * i + 2]))) * sc;
         const double* c = coeff + 11 * i;
         in.dimx = L(S(c[0])); in.dimy = L(S(c[1])); in.dimz = L(S(c[2]));
         in.c_drag = L(S(c[3])); in.c_drag_ang = L(S(c[4]));
