@@ -131,24 +131,34 @@ def physical_gpu_index(local_rank):
 
 
 # --------------------------------------------------------------------------------------------
+def host_threads():
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1: override it)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(sample_bodies, min_seconds=10.0, max_reps=200):
     """The oracle port (oracle/hydro_oracle.c, OpenMP over bodies) on the box's host cores."""
     from oracle import hydro_oracle as O
     from silver2_isaacsim_b200 import workloads as W
 
+    nthr = host_threads()
+
     wl = W.heterogeneous_boxes(sample_bodies)
     args = (wl.ctor_rows(), wl.masses(), wl.pos.astype(np.float64), wl.quat_xyzw.astype(np.float64),
             wl.lin_vel.astype(np.float64), wl.ang_vel.astype(np.float64), wl.prev_lin.astype(np.float64),
             wl.prev_ang.astype(np.float64), wl.dt)
-    O.step(*args)  # warm-up (page faults, OpenMP pool)
+    O.step(*args, n_threads=nthr)  # warm-up (page faults, OpenMP pool)
     reps, t0 = 0, time.perf_counter()
     while True:
-        O.step(*args)
+        O.step(*args, n_threads=nthr)
         reps += 1
         el = time.perf_counter() - t0
         if (el >= min_seconds and reps >= 3) or reps >= max_reps:
             break
-    return {"value": sample_bodies * reps / el, "unit": UNIT, "cores": O.max_threads(), "kind": "port",
+    return {"value": sample_bodies * reps / el, "unit": UNIT, "cores": nthr, "kind": "port",
             "sample": f"{reps} passes over {sample_bodies} C3 bodies ({el:.1f} s), float64, "
                       f"C restatement of the Numba path + behaviour tail, OpenMP"}
 
@@ -168,14 +178,14 @@ def run_reference(args):
          wl.lin_vel.astype(np.float64), wl.ang_vel.astype(np.float64), wl.prev_lin.astype(np.float64),
          wl.prev_ang.astype(np.float64), wl.dt)
     steps = max(1, min(args.steps, 400))
+    cores = host_threads()
     for _ in range(max(1, min(args.warmup, 5))):
-        O.step(*a)
+        O.step(*a, n_threads=cores)
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.step(*a)
+        O.step(*a, n_threads=cores)
     el = time.perf_counter() - t0
     value = sample * steps / el
-    cores = O.max_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / steps, "higher_is_better": True,
