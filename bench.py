@@ -293,6 +293,21 @@ def side_measurements(torch, W, dev, dtype_main):
     ms = timeit(lambda: e.step_bound(wl.dt), 200)
     out["c2_hexapod_4096_envs"] = {"bodies": wl.n, "us_per_step": 1e3 * ms, "updates_per_s": wl.n / (ms * 1e-3),
                                    "kernel": e.last_kernel, "note": "L2-resident (9.7 MB), launch-latency bound"}
+    # C4 per-GPU shard at 8 GPUs: 110 592 robots x 19 bodies, per-body records (+-20 % per-robot
+    # jitter), per-robot wrench by segmented warp shuffle inside the tile kernel
+    wl4 = W.sharded_robots(110592)
+    e4a, e4b = bound_engine(wl4, torch.float32, True), bound_engine(W.sharded_robots(110592, seed=W.SEED_BASE + 44), torch.float32, True)
+    k4s = [0]
+
+    def f4s():
+        (e4a if k4s[0] % 2 == 0 else e4b).step_bound(wl4.dt)
+        k4s[0] += 1
+    ms = timeit(f4s, 100)
+    bytes4 = (BYTES_PER_BODY_F32 + 24.0 / 19.0) * wl4.n
+    out["c4_shard_110592_robots"] = {"bodies": wl4.n, "us_per_step": 1e3 * ms, "updates_per_s": wl4.n / (ms * 1e-3),
+                                     "achieved_gbs": bytes4 / (ms * 1e-3) / 1e9, "kernel": e4a.last_kernel,
+                                     "note": "tiles of 76 bodies (4 robots) on 128-thread CTAs; 2 batches alternated"}
+    del e4a, e4b
     # C5: 1024 bodies, 1000-step rollout: per-step launches vs one captured CUDA graph
     wl5 = W.uniform_small_batch(1024)
     e5 = bound_engine(wl5, torch.float32, False)
@@ -436,6 +451,9 @@ def run_b200(args):
                        "l2": f"inputs larger than L2: {args.batches} independent batches x "
                              f"{bpb * n / 1e6:.0f} MB cycled, no flush needed",
                        "launch": launch_mode,
+                       "precision": "fp32 storage/traffic; fp32 arithmetic with the waterline, submersion ratio, "
+                                    "buoyancy and buoyancy arm carried in fp64 (DESIGN.md section 4)"
+                                    if args.dtype == "f32" else "fp64 storage and arithmetic",
                        "parallelism": f"env-sharded x{world}, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,

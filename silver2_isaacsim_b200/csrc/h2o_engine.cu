@@ -921,13 +921,33 @@ int h2o_step_host(h2o_handle h, const void* pos, const void* quat, const void* l
                                          : tile_bodies_for(DefaultCfg<double>::type::kThreads, 8, bpr);
     if (unit <= 0) unit = bpr > 0 ? bpr : 256;
     if (e->n_slots > 1) unit = unit / gcd_ll(unit, e->n_slots) * e->n_slots;  // keep slot phase per chunk
-    long long chunk = (e->n + 4 * HOST_PIPE_STREAMS - 1) / (4 * HOST_PIPE_STREAMS);
-    chunk = std::max<long long>(unit, (chunk + unit - 1) / unit * unit);
-    chunk = std::max<long long>(chunk, (65536 + unit - 1) / unit * unit);
+    // Chunk plan: the PCIe link is the bottleneck (H2D 52 B + D2H 24 B per body, full duplex), so
+    // the H2D engine must never idle and the un-overlapped tail (kernel + D2H of the LAST chunk)
+    // must be short: a few large chunks, tapered towards the end.
+    int n_chunks = 4;
+    if (const char* v = getenv("H2O_HOST_CHUNKS")) n_chunks = std::max(1, std::min(64, atoi(v)));
+    std::vector<long long> bounds(1, 0);
+    {
+        double wsum = 0;
+        std::vector<double> wgt(n_chunks);
+        for (int k = 0; k < n_chunks; ++k) {
+            wgt[k] = (k + 2 >= n_chunks && n_chunks > 2) ? (k + 1 == n_chunks ? 0.45 : 0.8) : 1.0;
+            wsum += wgt[k];
+        }
+        double acc = 0;
+        for (int k = 0; k < n_chunks; ++k) {
+            acc += wgt[k];
+            long long b = (long long)(double(e->n) * acc / wsum);
+            b = std::min<long long>(e->n, (b + unit - 1) / unit * unit);
+            if (k + 1 == n_chunks) b = e->n;
+            if (b > bounds.back()) bounds.push_back(b);
+        }
+        if (bounds.back() != e->n) bounds.push_back(e->n);
+    }
 
-    int k = 0;
-    for (long long b0 = 0; b0 < e->n; b0 += chunk, ++k) {
-        const long long cnt = std::min<long long>(chunk, e->n - b0);
+    for (size_t k = 0; k + 1 < bounds.size(); ++k) {
+        const long long b0 = bounds[k];
+        const long long cnt = bounds[k + 1] - b0;
         cudaStream_t s = e->hp_stream[k % HOST_PIPE_STREAMS];
         for (int i = 0; i < 4; ++i) {
             const size_t off = size_t(b0) * per_in[i] * e->esz;

@@ -344,3 +344,31 @@ def test_full_size_properties(dev):
     e.set_prev(ten[2], ten[3])
     F3, T3 = e.step(*ten, wl.dt)
     assert torch.equal(F2, F3) and torch.equal(T2, T3)
+
+
+def test_degenerate_inputs_stay_finite(dev):
+    """Zero quaternion, zero velocity, zero-size box, huge depth, NaN state: no crash, NaN is counted."""
+    from silver2_isaacsim_b200 import H2OError, HydroEngine
+
+    with pytest.raises(H2OError, match="BAD_ARGUMENT"):
+        HydroEngine(0, device=dev)  # empty engine is rejected at the boundary
+    n = 8
+    e = HydroEngine(n, device=dev)
+    coeff = np.tile(np.array(P.HydroParams().coeff_record(512.5)), (n, 1))
+    coeff[1, :3] = 0.0            # zero-size box
+    coeff[2, 10] = 0.0            # zero mass -> clamp forces everything to ~0
+    e.set_params_per_body(coeff)
+    e.enable_stats(True)
+    pos = torch.zeros(n, 3, device=dev); pos[:, 2] = -0.2; pos[3, 2] = -1e6
+    quat = torch.zeros(n, 4, device=dev); quat[:, 3] = 1.0; quat[4] = 0.0   # body 4: zero quaternion
+    v = torch.zeros(n, 3, device=dev); v[5] = torch.tensor([1e-7, 0, 0])   # body 5: below the speed threshold
+    w = torch.zeros(n, 3, device=dev)
+    pos[6, 0] = float("nan"); v[7, 2] = float("nan")
+    F, T = e.step(pos, quat, v, w, 1 / 60)
+    assert torch.isfinite(F[:6]).all() and torch.isfinite(T[:6]).all()
+    assert torch.isfinite(F[6]).all()          # x,y position never enters the wrench
+    assert not torch.isfinite(F[7]).all()      # a NaN velocity propagates ...
+    s = e.stats()
+    assert s["bodies"] == n and s["nonfinite_bodies"] == 1   # ... and is counted
+    assert s["still_wet_bodies"] >= 5          # wet and at rest: where the reference raises TypeError
+    assert (F[2].abs() <= 1e-5).all()          # zero mass: clamp scale = 0 * 500 / |F|
