@@ -306,7 +306,7 @@ def side_measurements(torch, W, dev, dtype_main):
     bytes4 = (BYTES_PER_BODY_F32 + 24.0 / 19.0) * wl4.n
     out["c4_shard_110592_robots"] = {"bodies": wl4.n, "us_per_step": 1e3 * ms, "updates_per_s": wl4.n / (ms * 1e-3),
                                      "achieved_gbs": bytes4 / (ms * 1e-3) / 1e9, "kernel": e4a.last_kernel,
-                                     "note": "tiles of 76 bodies (4 robots) on 128-thread CTAs; 2 batches alternated"}
+                                     "note": "tiles of 152 bodies (8 robots) on 160-thread CTAs; 2 batches alternated"}
     del e4a, e4b
     # C5: 1024 bodies, 1000-step rollout: per-step launches vs one captured CUDA graph
     wl5 = W.uniform_small_batch(1024)

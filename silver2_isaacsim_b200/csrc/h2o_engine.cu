@@ -88,7 +88,6 @@ struct h2o_engine {
     void* hp_dev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // pos quat lin ang F T W
     void* hp_pin[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaStream_t hp_stream[HOST_PIPE_STREAMS] = {nullptr, nullptr, nullptr};
-    cudaEvent_t hp_prev_ready = nullptr;
     cudaStream_t capture_stream = nullptr;  // graph capture never runs on the caller's (maybe legacy) stream
 };
 
@@ -129,6 +128,20 @@ template <int T, int I, int O, int MB, bool CO = false> struct Cfg {
 template <typename S> struct DefaultCfg;
 template <> struct DefaultCfg<float> { using type = Cfg<128, 1, 2, 6>; };
 template <> struct DefaultCfg<double> { using type = Cfg<64, 1, 2, 6>; };
+// With an articulation a tile holds whole robots (and whole 16-byte granules), e.g. 19-body
+// hexapods -> multiples of 76 bodies.  Several CTA sizes are compiled and the one whose lanes are
+// best used is picked per bodies_per_robot (19: 160 threads carry 152 bodies = 95 %).
+template <typename S> struct RobotCfgs;
+template <> struct RobotCfgs<float> {
+    using A = Cfg<128, 1, 2, 6>;
+    using B = Cfg<160, 1, 2, 4>;
+    using C = Cfg<256, 1, 2, 3>;
+};
+template <> struct RobotCfgs<double> {
+    using A = Cfg<64, 1, 2, 6>;
+    using B = Cfg<96, 1, 2, 4>;
+    using C = Cfg<160, 1, 2, 2>;
+};
 
 template <typename S, int kLayout, int kParam, bool kRobot, bool kStats, typename C> struct TileLaunch {
     using SM = TileSmem<S, kLayout, kParam, C::kThreads, C::kIn, C::kOut>;
@@ -213,7 +226,21 @@ static int launch_direct(h2o_engine* e, const StepArgs& a, long long body_begin,
     const long long cnt = a.n - body_begin;
     if (cnt <= 0) return H2O_OK;
     const int grid = int((cnt + 255) / 256);
-    step_direct_kernel<S, kLayout, kParam, kStats><<<grid, 256, 0, stream>>>(a, body_begin);
+    if (e->use_pdl) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(256);
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, step_direct_kernel<S, kLayout, kParam, kStats>, a, body_begin));
+    } else {
+        step_direct_kernel<S, kLayout, kParam, kStats><<<grid, 256, 0, stream>>>(a, body_begin);
+    }
     CUDA_TRY(cudaGetLastError());
     e->launches += 1;
     return H2O_OK;
@@ -237,7 +264,8 @@ static int step_typed2(h2o_engine* e, StepArgs& a, cudaStream_t stream)
 {
     using DC = typename DefaultCfg<S>::type;
     const bool robots = a.bodies_per_robot > 0 && a.out_wrench != nullptr;
-    const int TB = tile_bodies_for(DC::kThreads, sizeof(S), robots ? a.bodies_per_robot : 0);
+    const int TB = robots ? tile_bodies_for(RobotCfgs<S>::C::kThreads, sizeof(S), a.bodies_per_robot)
+                          : tile_bodies_for(DC::kThreads, sizeof(S), 0);
     bool ptr_ok = aligned16(a.pos) && aligned16(a.lin) && aligned16(a.prev) && aligned16(a.out_force) &&
                   aligned16(a.out_torque) && (kLayout == LAYOUT_PHYSX || (aligned16(a.quat) && aligned16(a.ang))) &&
                   (kParam == PARAM_TABLE || aligned16(a.coeff));
@@ -275,8 +303,18 @@ static int step_typed2(h2o_engine* e, StepArgs& a, cudaStream_t stream)
           }
         }
         if (!launched) {
-            rc = robots ? launch_tile<S, kLayout, kParam, true, kStats, DC>(e, a, stream)
-                        : launch_tile<S, kLayout, kParam, false, kStats, DC>(e, a, stream);
+            if (!robots) {
+                rc = launch_tile<S, kLayout, kParam, false, kStats, DC>(e, a, stream);
+            } else {
+                using RC = RobotCfgs<S>;
+                const int bpr = a.bodies_per_robot;
+                const double ua = double(tile_bodies_for(RC::A::kThreads, sizeof(S), bpr)) / RC::A::kThreads;
+                const double ub = double(tile_bodies_for(RC::B::kThreads, sizeof(S), bpr)) / RC::B::kThreads;
+                const double uc = double(tile_bodies_for(RC::C::kThreads, sizeof(S), bpr)) / RC::C::kThreads;
+                if (ua >= ub - 0.03 && ua >= uc - 0.06) rc = launch_tile<S, kLayout, kParam, true, kStats, typename RC::A>(e, a, stream);
+                else if (ub >= uc - 0.03) rc = launch_tile<S, kLayout, kParam, true, kStats, typename RC::B>(e, a, stream);
+                else rc = launch_tile<S, kLayout, kParam, true, kStats, typename RC::C>(e, a, stream);
+            }
         }
         if (rc) return rc;
         done_bodies = (long long)a.n_tiles * a.tile_bodies;
@@ -420,7 +458,6 @@ int h2o_destroy(h2o_handle h)
     }
     for (int i = 0; i < HOST_PIPE_STREAMS; ++i)
         if (e->hp_stream[i]) cudaStreamDestroy(e->hp_stream[i]);
-    if (e->hp_prev_ready) cudaEventDestroy(e->hp_prev_ready);
     if (e->capture_stream) cudaStreamDestroy(e->capture_stream);
     if (e->coeff) cudaFree(e->coeff);
     if (e->slot_type) cudaFree(e->slot_type);
@@ -861,7 +898,6 @@ static int hp_init(h2o_engine* e)
         CUDA_TRY(cudaMalloc(&e->hp_dev[i], bytes));
     }
     for (int i = 0; i < HOST_PIPE_STREAMS; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&e->hp_stream[i], cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreateWithFlags(&e->hp_prev_ready, cudaEventDisableTiming));
     return H2O_OK;
 }
 
@@ -917,9 +953,8 @@ int h2o_step_host(h2o_handle h, const void* pos, const void* quat, const void* l
 
     // chunking: whole tiles / whole robots per chunk, a few chunks per stream
     const int bpr = (out_robot_wrench && e->bodies_per_robot > 0) ? e->bodies_per_robot : 0;
-    long long unit = e->dtype == H2O_F32 ? tile_bodies_for(DefaultCfg<float>::type::kThreads, 4, bpr)
-                                         : tile_bodies_for(DefaultCfg<double>::type::kThreads, 8, bpr);
-    if (unit <= 0) unit = bpr > 0 ? bpr : 256;
+    long long unit = tile_unit(e->esz, bpr);
+    while (unit < 256) unit *= 2;  // whole robots and whole 16-byte granules per chunk
     if (e->n_slots > 1) unit = unit / gcd_ll(unit, e->n_slots) * e->n_slots;  // keep slot phase per chunk
     // Chunk plan: the PCIe link is the bottleneck (H2D 52 B + D2H 24 B per body, full duplex), so
     // the H2D engine must never idle and the un-overlapped tail (kernel + D2H of the LAST chunk)

@@ -290,9 +290,12 @@ __device__ __forceinline__ void flush_stats(const ThreadStats& st, double* stats
 // Segmented warp-shuffle reduction: net wrench per robot (articulation).
 // Lanes hold consecutive bodies; `seg` is the robot index within the tile.
 // After the scan the first lane of each segment in the warp owns the partial
-// sum of that warp's slice of the robot and adds it to the tile accumulator.
+// sum of that warp's slice of the robot and adds it to the tile accumulator
+// (a robot of <= 32 bodies spans at most two warps: two commutative adds).
+// Reduction precision = storage precision (fp32 mode: float, fp64 mode: double).
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void robot_reduce_warp(double v[6], int seg, bool active, double* acc /*[robots][6]*/)
+template <typename A>
+__device__ __forceinline__ void robot_reduce_warp(A v[6], int seg, bool active, A* acc /*[robots][6]*/)
 {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -303,7 +306,7 @@ __device__ __forceinline__ void robot_reduce_warp(double v[6], int seg, bool act
         const bool take = (lane + o < 32) && (k2 == key);
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
-            const double u = __shfl_down_sync(full, v[c], o);
+            const A u = __shfl_down_sync(full, v[c], o);
             if (take) v[c] += u;
         }
     }
@@ -338,7 +341,7 @@ struct TileSmem {
     static constexpr size_t OUT_BYTES = size_t(TL::E_OUT) * kThreads * sizeof(S);
     static constexpr size_t TABLE_BYTES =
         (kParam == PARAM_TABLE) ? (size_t(MAX_TABLE_TYPES) * N_COEFF * sizeof(S) + MAX_TABLE_SLOTS) : 0;
-    static constexpr size_t ROBOT_BYTES = size_t(kThreads) * 6 * sizeof(double);  // <= kThreads robots/tile
+    static constexpr size_t ROBOT_BYTES = size_t(kThreads) * 6 * sizeof(S);  // <= kThreads robots/tile
     static constexpr size_t BAR_BYTES = 16 * sizeof(uint64_t);
     static constexpr size_t OFF_IN = 0;
     static constexpr size_t OFF_OUT = OFF_IN + kStagesIn * IN_BYTES;
@@ -371,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
     const int TB = a.tile_bodies;  // bodies per tile (<= kThreads)
     S* const table = reinterpret_cast<S*>(smem + SM::OFF_TABLE);
     unsigned char* const slot_map = smem + SM::OFF_TABLE + size_t(MAX_TABLE_TYPES) * N_COEFF * sizeof(S);
-    double* const robot_acc = reinterpret_cast<double*>(smem + SM::OFF_ROBOT);
+    S* const robot_acc = reinterpret_cast<S*>(smem + SM::OFF_ROBOT);
     uint64_t* const full_bar =
         reinterpret_cast<uint64_t*>(smem + SM::OFF_ROBOT + (kRobot ? SM::ROBOT_BYTES : 0));
 
@@ -443,7 +446,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
         const int robots_in_tile = kRobot ? cnt / bpr : 0;
         if (kRobot) {
             // same thread <-> same index as the read-out loop below: no barrier needed in between
-            for (int i = tid; i < robots_in_tile * 6; i += kThreads) robot_acc[i] = 0.0;
+            for (int i = tid; i < robots_in_tile * 6; i += kThreads) robot_acc[i] = S(0);
         }
         mbar_wait(&full_bar[stage], (it / kStagesIn) & 1);
 
@@ -512,15 +515,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
         }
         if (kRobot) {
             // wrench about the robot's slot-0 body: tau_i + (p_i - p_base) x F_i
-            double v[6] = {0, 0, 0, 0, 0, 0};
+            S v[6] = {S(0), S(0), S(0), S(0), S(0), S(0)};
             if (active) {
-                const double ax = double(r.px) - double(basex), ay = double(r.py) - double(basey),
-                             az = double(r.pz) - double(basez);
-                const double fx = double(F[0]), fy = double(F[1]), fz = double(F[2]);
-                v[0] = fx; v[1] = fy; v[2] = fz;
-                v[3] = double(T[0]) + (ay * fz - az * fy);
-                v[4] = double(T[1]) + (az * fx - ax * fz);
-                v[5] = double(T[2]) + (ax * fy - ay * fx);
+                const S ax = r.px - basex, ay = r.py - basey, az = r.pz - basez;
+                v[0] = F[0]; v[1] = F[1]; v[2] = F[2];
+                v[3] = T[0] + (ay * F[2] - az * F[1]);
+                v[4] = T[1] + (az * F[0] - ax * F[2]);
+                v[5] = T[2] + (ax * F[1] - ay * F[0]);
             }
             robot_reduce_warp(v, seg, active, robot_acc);
         }
@@ -536,7 +537,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
         }
         if (kRobot) {
             S* ow = reinterpret_cast<S*>(a.out_wrench) + (tile_begin / bpr) * 6;
-            for (int i = tid; i < robots_in_tile * 6; i += kThreads) ow[i] = S(robot_acc[i]);
+            for (int i = tid; i < robots_in_tile * 6; i += kThreads) ow[i] = robot_acc[i];
         }
     }
     if (tid == 0) bulk_wait_all<0>();
@@ -553,6 +554,8 @@ __global__ void __launch_bounds__(256) step_direct_kernel(const __grid_constant_
 {
     __shared__ S table[(kParam == PARAM_TABLE) ? MAX_TABLE_TYPES * N_COEFF : 1];
     __shared__ unsigned char slot_map[(kParam == PARAM_TABLE) ? MAX_TABLE_SLOTS : 1];
+    pdl_launch_dependents();   // no-ops unless launched with the PDL attribute
+    pdl_wait_prerequisites();
     if (kParam == PARAM_TABLE) {
         const S* g = reinterpret_cast<const S*>(a.coeff);
         for (int i = threadIdx.x; i < a.n_types * N_COEFF; i += blockDim.x) table[i] = g[i];

@@ -306,8 +306,23 @@ def test_error_codes(dev):
 
 
 # --------------------------------------------------------------------------- full-size properties
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["fp32", "fp64"])
+def test_full_size_oracle_parity(oracle, dev, dtype):
+    """BASELINE config 3 at full size: every one of the 2^20 bodies against the float64 oracle."""
+    wl = W.heterogeneous_boxes(1 << 20)
+    ref = _ref(oracle, wl)
+    e = _engine(wl, dtype, dev, "tile")
+    F, T = _run_step(e, wl, dtype, dev)
+    assert e.last_kernel == "tile"
+    _check(wl, dtype, ref, F, T, "C3 2^20")
+    wet = ref.components["sub_ratio"] > 0
+    partial = wet & (ref.components["sub_ratio"] < 1)
+    assert 0.3 < wet.mean() < 0.95 and partial.mean() > 0.2      # the wet / partial / dry mix of SURVEY 8(d)
+    assert (F[~wet] == 0).all() and (T[~wet] == 0).all()          # dry bodies: exact zeros
+
+
 def test_full_size_properties(dev):
-    """BASELINE size (2^20 bodies): size-independent properties instead of an oracle pass."""
+    """BASELINE size (2^20 bodies): size-independent properties of the fused step."""
     wl = W.heterogeneous_boxes(1 << 20)
     e = _engine(wl, torch.float32, dev, "tile")
     ten = [_t(a, torch.float32, dev) for a in (wl.pos, wl.quat_xyzw, wl.lin_vel, wl.ang_vel)]

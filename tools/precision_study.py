@@ -1,37 +1,33 @@
-"""Precision study (CPU only): model header (host-instantiated) vs the f64 oracle."""
-import ctypes, os, sys, time
+"""Precision study on the CPU: the model header (host-instantiated, tests/host_emul) vs the f64 oracle.
+
+    python tools/precision_study.py [n_bodies]
+
+Prints, per workload and precision policy, how many force / torque vectors miss the fp32
+criterion of SURVEY.md 8(d) and the error quantiles.  This is how the mixed-precision policy of
+DESIGN.md section 4 was chosen (fp32 storage; waterline, ratio, buoyancy and buoyancy arm in fp64).
+"""
+import os
+import sys
+
 import numpy as np
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import hydro_oracle as O
-from silver2_isaacsim_b200 import workloads as W
+from oracle import hydro_oracle as O  # noqa: E402
+from silver2_isaacsim_b200 import workloads as W  # noqa: E402
+from tests import emul, scoring  # noqa: E402
 
-E = ctypes.CDLL(os.path.join(os.path.dirname(__file__), '..', 'tests', '_emul', 'libh2o_emul.so'))
-def P(a): return a.ctypes.data_as(ctypes.c_void_p)
-
-def emul(wl, mode, exact):
-    n = wl.n
-    d = lambda a: np.ascontiguousarray(a, dtype=np.float64)
-    F = np.zeros((n,3)); T = np.zeros((n,3)); comp = np.zeros((n,28)); masks = np.zeros(n, np.uint32)
-    arrs = [d(wl.pos), d(wl.quat_xyzw), d(wl.lin_vel), d(wl.ang_vel), d(wl.prev_lin), d(wl.prev_ang), d(wl.coeff_per_body())]
-    E.emul_step(mode, exact, ctypes.c_int64(n), *[P(a) for a in arrs], ctypes.c_double(wl.rho), ctypes.c_double(wl.g),
-                ctypes.c_double(wl.dt), P(F), P(T), P(comp), P(masks))
-    return F, T, comp, masks
-
-def score(x, y, rel, abs_):
-    err = np.abs(x-y).max(axis=1); den = np.abs(y).max(axis=1)
-    tol = np.maximum(rel*den, abs_)
-    return err, den, err > tol
-
-if __name__ == '__main__':
+if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
-    for name, wl in [('C3', W.heterogeneous_boxes(n)), ('C2', W.hexapod_envs(n//19))]:
-        t=time.time()
-        ref = O.step(wl.ctor_rows(), wl.masses(), wl.pos, wl.quat_xyzw, wl.lin_vel, wl.ang_vel, wl.prev_lin, wl.prev_ang, wl.dt)
-        print(name, 'n', wl.n, 'oracle %.2fs'%(time.time()-t), 'raises', int((ref.flags&1).sum()), 'clamped', int((ref.flags&2).sum()>>1))
-        for mode, exact, label, rel, ab in [(1,0,'fp32-mixed',1e-5,1e-6),(2,0,'fp32-all',1e-5,1e-6),(3,0,'fp32store-f64arith',1e-5,1e-6)]:
-            F,T,comp,masks = emul(wl, mode, exact)
-            for nm,x,y in [('F',F,ref.force),('T',T,ref.torque)]:
-                err,den,bad = score(x,y,rel,ab)
-                relerr = err/np.maximum(den,1e-30)
-                wet = den>0
-                print(f'  {label:20s} {nm}: fail {int(bad.sum()):6d}/{wl.n}  median rel {np.median(relerr[wet]):.2e} p99.9 {np.quantile(relerr[wet],0.999):.2e} max rel {relerr[wet].max():.2e} max abs {err.max():.2e}')
+    for name, wl in (("C3", W.heterogeneous_boxes(n)), ("C2", W.hexapod_envs(n // 19)),
+                     ("C4", W.sharded_robots(n // 38)), ("C5", W.uniform_small_batch(min(n, 100000)))):
+        ref = O.step(wl.ctor_rows(), wl.masses(), wl.pos, wl.quat_xyzw, wl.lin_vel, wl.ang_vel, wl.prev_lin,
+                     wl.prev_ang, wl.dt)
+        for mode, label in ((emul.MODE_FP32_FAST, "fp32 fused step (kernel path)"), (emul.MODE_FP32, "fp32 generic"),
+                            (emul.MODE_ALL_FP32, "all-fp32 arithmetic"), (emul.MODE_FP32_STORE_FP64_MATH, "fp32 storage, fp64 math")):
+            F, T, _, _ = emul.step(wl, mode)
+            for nm, x, y in (("F", F, ref.force), ("T", T, ref.torque)):
+                err, den = scoring.vec_err(x, y)
+                tol = np.maximum(1e-5 * den, 1e-6)
+                rel = err[den > 0] / den[den > 0]
+                print(f"{name} {label:30s} {nm}: miss {int((err > tol).sum()):5d}/{wl.n}  median {np.median(rel):.2e} "
+                      f"p99.9 {np.quantile(rel, 0.999):.2e}  worst {float((err / tol).max()):.2f}x tol")
