@@ -70,6 +70,7 @@ struct h2o_engine {
     int sm_count = 148;
     int tile_cfg = 0;          // 0 = default configuration of the dtype
     int max_ctas_per_sm = 0;   // 0 = as many as fit
+    int robot_cfg = -1;        // -1 = pick the CTA size by lane utilisation (tuning override: 0,1,2)
     bool use_pdl = false;      // programmatic dependent launch of the tile kernel
     int rollout_free_bodies = 0;  // 1: rollouts integrate the bound state between steps (free bodies)
     double rollout_gravity = 9.81;
@@ -311,8 +312,10 @@ static int step_typed2(h2o_engine* e, StepArgs& a, cudaStream_t stream)
                 const double ua = double(tile_bodies_for(RC::A::kThreads, sizeof(S), bpr)) / RC::A::kThreads;
                 const double ub = double(tile_bodies_for(RC::B::kThreads, sizeof(S), bpr)) / RC::B::kThreads;
                 const double uc = double(tile_bodies_for(RC::C::kThreads, sizeof(S), bpr)) / RC::C::kThreads;
-                if (ua >= ub - 0.03 && ua >= uc - 0.06) rc = launch_tile<S, kLayout, kParam, true, kStats, typename RC::A>(e, a, stream);
-                else if (ub >= uc - 0.03) rc = launch_tile<S, kLayout, kParam, true, kStats, typename RC::B>(e, a, stream);
+                int pick = (ua >= ub - 0.03 && ua >= uc - 0.06) ? 0 : (ub >= uc - 0.03 ? 1 : 2);
+                if (e->robot_cfg >= 0) pick = e->robot_cfg;
+                if (pick == 0) rc = launch_tile<S, kLayout, kParam, true, kStats, typename RC::A>(e, a, stream);
+                else if (pick == 1) rc = launch_tile<S, kLayout, kParam, true, kStats, typename RC::B>(e, a, stream);
                 else rc = launch_tile<S, kLayout, kParam, true, kStats, typename RC::C>(e, a, stream);
             }
         }
@@ -432,6 +435,7 @@ int h2o_create(h2o_handle* out, int64_t n_bodies, int dtype, int device)
     e->sm_count = prop.multiProcessorCount;
     if (const char* v = getenv("H2O_MAX_CTAS_PER_SM")) e->max_ctas_per_sm = atoi(v);
     if (const char* v = getenv("H2O_PDL")) e->use_pdl = atoi(v) != 0;
+    if (const char* v = getenv("H2O_ROBOT_CFG")) e->robot_cfg = std::max(-1, std::min(2, atoi(v)));
     if (cudaMalloc(&e->prev, size_t(n_bodies) * 6 * e->esz) != cudaSuccess ||
         cudaMalloc(reinterpret_cast<void**>(&e->stats), N_STATS * sizeof(double)) != cudaSuccess) {
         cudaGetLastError();

@@ -16,7 +16,7 @@
 //                      through shared memory and TMA bulk stores.  Row-major
 //                      (N,3)/(N,4)/(N,6)/(N,7)/(N,11) caller layouts therefore cost
 //                      no uncoalesced or partial-sector traffic.  Optional
-//                      per-robot wrench: segmented warp-shuffle reduction.
+//                      per-robot wrench summed out of shared memory.
 //   step_direct_kernel one thread per body, plain global loads; used for small
 //                      batches (latency-bound), unaligned pointers and the
 //                      full-signature `components` entry point.
@@ -287,38 +287,6 @@ __device__ __forceinline__ void flush_stats(const ThreadStats& st, double* stats
 }
 
 // ---------------------------------------------------------------------------
-// Segmented warp-shuffle reduction: net wrench per robot (articulation).
-// Lanes hold consecutive bodies; `seg` is the robot index within the tile.
-// After the scan the first lane of each segment in the warp owns the partial
-// sum of that warp's slice of the robot and adds it to the tile accumulator
-// (a robot of <= 32 bodies spans at most two warps: two commutative adds).
-// Reduction precision = storage precision (fp32 mode: float, fp64 mode: double).
-// ---------------------------------------------------------------------------
-template <typename A>
-__device__ __forceinline__ void robot_reduce_warp(A v[6], int seg, bool active, A* acc /*[robots][6]*/)
-{
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int key = active ? seg : -1 - lane;  // inactive lanes never match a neighbour
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int k2 = __shfl_down_sync(full, key, o);
-        const bool take = (lane + o < 32) && (k2 == key);
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-            const A u = __shfl_down_sync(full, v[c], o);
-            if (take) v[c] += u;
-        }
-    }
-    const int kprev = __shfl_up_sync(full, key, 1);
-    const bool head = active && (lane == 0 || kprev != key);
-    if (head) {
-#pragma unroll
-        for (int c = 0; c < 6; ++c) atomicAdd(&acc[seg * 6 + c], v[c]);
-    }
-}
-
-// ---------------------------------------------------------------------------
 // Shared-memory tile layout
 // ---------------------------------------------------------------------------
 template <typename S, int kLayout, int kParam> struct TileLayout {
@@ -341,7 +309,7 @@ struct TileSmem {
     static constexpr size_t OUT_BYTES = size_t(TL::E_OUT) * kThreads * sizeof(S);
     static constexpr size_t TABLE_BYTES =
         (kParam == PARAM_TABLE) ? (size_t(MAX_TABLE_TYPES) * N_COEFF * sizeof(S) + MAX_TABLE_SLOTS) : 0;
-    static constexpr size_t ROBOT_BYTES = size_t(kThreads) * 6 * sizeof(S);  // <= kThreads robots/tile
+    static constexpr size_t ROBOT_BYTES = size_t(kThreads) * 3 * sizeof(S);  // transferred torques, [3][tile]
     static constexpr size_t BAR_BYTES = 16 * sizeof(uint64_t);
     static constexpr size_t OFF_IN = 0;
     static constexpr size_t OFF_OUT = OFF_IN + kStagesIn * IN_BYTES;
@@ -444,10 +412,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
         next_begin += round_stride;
         const bool active = tid < cnt;
         const int robots_in_tile = kRobot ? cnt / bpr : 0;
-        if (kRobot) {
-            // same thread <-> same index as the read-out loop below: no barrier needed in between
-            for (int i = tid; i < robots_in_tile * 6; i += kThreads) robot_acc[i] = S(0);
-        }
         mbar_wait(&full_bar[stage], (it / kStagesIn) & 1);
 
         const unsigned char* in = smem + SM::OFF_IN + size_t(stage) * SM::IN_BYTES;
@@ -462,7 +426,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
         RawBody<S> r;
         S cl[N_COEFF];
         S basex = S(0), basey = S(0), basez = S(0);
-        int seg = 0;
         if (active) {
             load_raw<S, kLayout>(bp, tid, r);
             const S* c;
@@ -479,8 +442,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
 #pragma unroll
             for (int k = 0; k < N_COEFF; ++k) cl[k] = c[k];
             if (kRobot) {
-                seg = tid / bpr;
-                const S* pb = bp.pos + TL::E_POS * (seg * bpr);
+                const S* pb = bp.pos + TL::E_POS * ((tid / bpr) * bpr);
                 basex = pb[0]; basey = pb[1]; basez = pb[2];
             }
         }
@@ -513,17 +475,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
             v.x = r.vz; v.y = r.wx; op[1] = v;
             v.x = r.wy; v.y = r.wz; op[2] = v;
         }
-        if (kRobot) {
-            // wrench about the robot's slot-0 body: tau_i + (p_i - p_base) x F_i
-            S v[6] = {S(0), S(0), S(0), S(0), S(0), S(0)};
-            if (active) {
-                const S ax = r.px - basex, ay = r.py - basey, az = r.pz - basez;
-                v[0] = F[0]; v[1] = F[1]; v[2] = F[2];
-                v[3] = T[0] + (ay * F[2] - az * F[1]);
-                v[4] = T[1] + (az * F[0] - ax * F[2]);
-                v[5] = T[2] + (ax * F[1] - ay * F[0]);
-            }
-            robot_reduce_warp(v, seg, active, robot_acc);
+        if (kRobot && active) {
+            // torque of body i about the robot's slot-0 body: tau_i + (p_i - p_base) x F_i, parked in
+            // shared memory ([component][body]) next to the forces already sitting in the output stage
+            const S ax = r.px - basex, ay = r.py - basey, az = r.pz - basez;
+            robot_acc[0 * TB + tid] = T[0] + (ay * F[2] - az * F[1]);
+            robot_acc[1 * TB + tid] = T[1] + (az * F[0] - ax * F[2]);
+            robot_acc[2 * TB + tid] = T[2] + (ax * F[1] - ay * F[0]);
         }
         fence_proxy_async_smem();
         __syncthreads();  // (C) results (and robot accumulators) complete
@@ -535,9 +493,22 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
             bulk_s2g(reinterpret_cast<S*>(a.prev) + tile_begin * 6, out + oo_prev, cb * 6);
             bulk_commit();
         }
-        if (kRobot) {
-            S* ow = reinterpret_cast<S*>(a.out_wrench) + (tile_begin / bpr) * 6;
-            for (int i = tid; i < robots_in_tile * 6; i += kThreads) ow[i] = robot_acc[i];
+        if (kRobot && tid < robots_in_tile * 6) {
+            // Per-robot net wrench: thread (robot, component) sums its robot's bodies straight out of
+            // shared memory in body order (deterministic; bank-conflict free for the strides involved).
+            // Measured on the C4 shard (profiles/r01_robot_wrench_variants.log): segmented warp-shuffle
+            // scan over all lanes + shared-memory atomics 80 us, this 68 us, lane pairs + shuffle 72 us.
+            // The scratch is rewritten only after the next tile's barrier (A), which these threads
+            // reach after the sum.  (robot_wrench_kernel -- tails, robots larger than a tile -- reduces
+            // one robot per warp with shuffles.)
+            const int rb = tid / 6, c = tid - 6 * rb;
+            const S* src = (c < 3) ? reinterpret_cast<const S*>(out) + 3 * (rb * bpr) + c
+                                   : robot_acc + (c - 3) * TB + rb * bpr;
+            const int step = (c < 3) ? 3 : 1;
+            S sum = S(0);
+#pragma unroll 4
+            for (int j = 0; j < bpr; ++j) sum += src[j * step];
+            reinterpret_cast<S*>(a.out_wrench)[(tile_begin / bpr) * 6 + tid] = sum;
         }
     }
     if (tid == 0) bulk_wait_all<0>();
