@@ -107,6 +107,11 @@ H2O_API int h2o_set_articulation(h2o_handle h, int bodies_per_robot);
  * (hydrodynamics_behavior.py:194); the wrappers themselves take xyzw. */
 H2O_API int h2o_set_quat_order(h2o_handle h, int order);
 H2O_API int h2o_set_kernel(h2o_handle h, int choice);
+/* h2o_components only: reproduce the behavioural deviations of the reference's Warp twin
+ * (warp_hydrodynamics.py): accelerations rotated forward instead of inverse
+ * for the added-mass terms (:216-217) and cob = cop = position for a dry body (:59-61, :290).
+ * Default 0 = the Numba semantics, which every other entry point always follows. */
+H2O_API int h2o_set_warp_compat(h2o_handle h, int enable);
 /* Tuning knob: tile-kernel variant (threads per CTA / TMA stages); 0 = built-in default. */
 H2O_API int h2o_set_tile_config(h2o_handle h, int cfg);
 /* Accumulate global statistics inside the step kernel (device-side, no host sync). */

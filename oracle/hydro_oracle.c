@@ -328,6 +328,13 @@ static void calculate_lift(double speed, const double vel_dir[3], const double r
     for (int k = 0; k < 3; ++k) lift[k] = lift_magnitude * dir[k] * sub_ratio;
 }
 
+/* Behavioural deviations of the reference's Warp twin (warp_hydrodynamics.py, SURVEY.md
+ * Appendix C), switchable so that the CUDA warp-compat mode has a checker too:
+ *   C1  accelerations are rotated FORWARD (quat_rotate) instead of by R^T (:216-217)
+ *   C3  a dry body returns cob = cop = position instead of zeros (:59-61, :290) */
+static int g_warp_compat = 0;
+ORACLE_API void oracle_set_warp_compat(int enable) { g_warp_compat = enable != 0; }
+
 /* numba_hydrodynamics.py:219-253 (calculate_added_mass); dense 6x6 matvec */
 static void calculate_added_mass(double sub_ratio, const double lin_acc[3], const double ang_acc[3],
                                  const double rot[3][3], const double M[6][6], double force[3],
@@ -337,8 +344,13 @@ static void calculate_added_mass(double sub_ratio, const double lin_acc[3], cons
     torque[0] = torque[1] = torque[2] = 0.0;
     if (sub_ratio <= 1e-9) return;
     double accel_6d[6];
-    matTvec3(rot, lin_acc, &accel_6d[0]);
-    matTvec3(rot, ang_acc, &accel_6d[3]);
+    if (g_warp_compat) {
+        matvec3(rot, lin_acc, &accel_6d[0]);
+        matvec3(rot, ang_acc, &accel_6d[3]);
+    } else {
+        matTvec3(rot, lin_acc, &accel_6d[0]);
+        matTvec3(rot, ang_acc, &accel_6d[3]);
+    }
     double ft[6];
     for (int i = 0; i < 6; ++i) {
         double acc = 0.0;
@@ -372,7 +384,13 @@ ORACLE_API void oracle_solve(const oracle_body_t *b, const double position[3],
     }
     double cob[3];
     const double sub_ratio = analyze_submersion_and_cob(wk, position, cob);
-    if (sub_ratio <= 1e-9) return; /* :277-279 -- every output zero, incl. cob/cop */
+    if (sub_ratio <= 1e-9) { /* :277-279 -- every output zero, incl. cob/cop */
+        if (g_warp_compat) {
+            memcpy(out->center_of_buoyancy, position, 3 * sizeof(double));
+            memcpy(out->center_of_pressure, position, 3 * sizeof(double));
+        }
+        return;
+    }
 
     out->sub_ratio = sub_ratio;
     out->buoyancy_force[2] = b->water_density * (sub_ratio * b->total_volume) * b->gravity;

@@ -74,6 +74,11 @@ def lib() -> ctypes.CDLL:
     return _lib
 
 
+def set_warp_compat(enable: bool) -> None:
+    """Switch the oracle to the Warp twin's deviations (C1, C3)."""
+    lib().oracle_set_warp_compat(ctypes.c_int(1 if enable else 0))
+
+
 def max_threads() -> int:
     return int(lib().oracle_max_threads())
 

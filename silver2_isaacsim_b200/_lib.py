@@ -54,6 +54,7 @@ SIGNATURES = {
     "h2o_set_quat_order": (c_int, [_P, c_int]),
     "h2o_set_kernel": (c_int, [_P, c_int]),
     "h2o_set_tile_config": (c_int, [_P, c_int]),
+    "h2o_set_warp_compat": (c_int, [_P, c_int]),
     "h2o_enable_stats": (c_int, [_P, c_int]),
     "h2o_reset": (c_int, [_P, _P]),
     "h2o_set_prev": (c_int, [_P, _P, _P, _P]),

@@ -70,6 +70,7 @@ struct h2o_engine {
     int sm_count = 148;
     int tile_cfg = 0;          // 0 = default configuration of the dtype
     int max_ctas_per_sm = 0;   // 0 = as many as fit
+    int warp_compat = 0;       // components entry point reproduces the Warp twin's deviations
     int robot_cfg = -1;        // -1 = pick the CTA size by lane utilisation (tuning override: 0,1,2)
     bool use_pdl = false;      // programmatic dependent launch of the tile kernel
     int rollout_free_bodies = 0;  // 1: rollouts integrate the bound state between steps (free bodies)
@@ -600,6 +601,14 @@ int h2o_set_kernel(h2o_handle h, int choice)
     return H2O_OK;
 }
 
+int h2o_set_warp_compat(h2o_handle h, int enable)
+{
+    h2o_engine* e = check(h);
+    if (!e) return H2O_ERR_BAD_HANDLE;
+    e->warp_compat = enable != 0;
+    return H2O_OK;
+}
+
 int h2o_set_tile_config(h2o_handle h, int cfg)
 {
     h2o_engine* e = check(h);
@@ -882,6 +891,7 @@ int h2o_components(h2o_handle h, const void* pos, const void* quat, const void* 
     a.n_slots = e->n_slots; a.n_types = e->n_types;
     a.param_mode = e->param_mode;
     a.quat_wxyz = e->quat_order == H2O_QUAT_WXYZ;
+    a.warp_compat = e->warp_compat;
     a.rho = e->rho; a.grav = e->grav;
     const int grid = int((e->n + 255) / 256);
     cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -212,6 +212,7 @@ __device__ __forceinline__ void make_body_in(const RawBody<S>& r, const S* c, in
     in.c_drag = c[3]; in.c_drag_ang = c[4]; in.k_damp = c[5]; in.k_damp_ang = c[6];
     in.c_am = c[7]; in.c_am_ang = c[8]; in.c_lift = c[9];
     in.rho_h = rho; in.grav_h = grav; in.rho = S(rho);
+    in.warp_compat = false;
 }
 
 // Running statistics kept in registers across a thread's bodies.
@@ -623,6 +624,7 @@ struct ComponentsArgs {
     int32_t* out_flags;  // (N,) bit0 = "reference raises" (wet, speed <= 1e-6), may be null
     long long n, first_body;
     int n_slots, n_types, param_mode, quat_wxyz;
+    int warp_compat;  // reproduce the deviations of the reference's Warp twin
     double rho, grav;
 };
 
@@ -651,9 +653,12 @@ __global__ void __launch_bounds__(256) components_kernel(const __grid_constant__
     in.ax = la[0]; in.ay = la[1]; in.az = la[2];
     in.bx = aa[0]; in.by = aa[1]; in.bz = aa[2];
     in.acc_scale = S(1);
+    in.warp_compat = a.warp_compat != 0;
     Terms<double, S> t;
     body_terms<double, S, false>(in, t);
-    const bool wet = t.ratio > 0.0;
+    // Numba: a dry body returns zeros everywhere, cob/cop included (numba_hydrodynamics.py:277-279);
+    // the Warp twin returns cob = cop = position (warp_hydrodynamics.py:59-61, :290)
+    const bool wet = t.ratio > 0.0 || a.warp_compat != 0;
     S* o;
     o = reinterpret_cast<S*>(a.out[0]) + 3 * i; o[0] = S(0); o[1] = S(0); o[2] = S(t.fbz);
     o = reinterpret_cast<S*>(a.out[1]) + 3 * i; o[0] = t.fd[0]; o[1] = t.fd[1]; o[2] = t.fd[2];

@@ -176,6 +176,8 @@ template <typename H, typename L> struct BodyIn {
     // coefficient record (params.py COEFF_FIELDS) + globals
     L dimx, dimy, dimz;
     L c_drag, c_drag_ang, k_damp, k_damp_ang, c_am, c_am_ang, c_lift;
+    bool warp_compat;     // body_terms only: rotate accelerations FORWARD into the "body" frame, as the
+                          // reference's Warp twin does (warp_hydrodynamics.py:216-217)
     H rho_h, grav_h;      // globals: waterDensity, gravity (H for buoyancy)
     L rho;                // = L(rho_h)
 };
@@ -388,9 +390,10 @@ H2O_HD void body_terms(const BodyIn<H, L>& in, Terms<H, L>& t)
     //      numba_hydrodynamics_wrapper.py:101-112): -R diag(M) R^T acc * ratio
     {
         const L ml = vol * in.c_am * in.rho * rl;
-        const L lx = r00 * in.ax + r10 * in.ay + r20 * in.az;
-        const L ly = r01 * in.ax + r11 * in.ay + r21 * in.az;
-        const L lz = r02 * in.ax + r12 * in.ay + r22 * in.az;
+        const bool fwd = in.warp_compat;  // Numba: R^T a (numba_hydrodynamics.py:229-230); Warp twin: R a
+        const L lx = fwd ? r00 * in.ax + r01 * in.ay + r02 * in.az : r00 * in.ax + r10 * in.ay + r20 * in.az;
+        const L ly = fwd ? r10 * in.ax + r11 * in.ay + r12 * in.az : r01 * in.ax + r11 * in.ay + r21 * in.az;
+        const L lz = fwd ? r20 * in.ax + r21 * in.ay + r22 * in.az : r02 * in.ax + r12 * in.ay + r22 * in.az;
         const L fx = -(ml * lx), fy = -(ml * ly), fz = -(ml * lz);
         t.fam[0] = r00 * fx + r01 * fy + r02 * fz;
         t.fam[1] = r10 * fx + r11 * fy + r12 * fz;
@@ -398,9 +401,9 @@ H2O_HD void body_terms(const BodyIn<H, L>& in, Terms<H, L>& t)
 
         const L ma = vol * in.c_am_ang * in.rho * rl;
         const L w2s = in.dimx * in.dimx, d2s = in.dimy * in.dimy, h2s = in.dimz * in.dimz;
-        const L gx = r00 * in.bx + r10 * in.by + r20 * in.bz;
-        const L gy = r01 * in.bx + r11 * in.by + r21 * in.bz;
-        const L gz = r02 * in.bx + r12 * in.by + r22 * in.bz;
+        const L gx = fwd ? r00 * in.bx + r01 * in.by + r02 * in.bz : r00 * in.bx + r10 * in.by + r20 * in.bz;
+        const L gy = fwd ? r10 * in.bx + r11 * in.by + r12 * in.bz : r01 * in.bx + r11 * in.by + r21 * in.bz;
+        const L gz = fwd ? r20 * in.bx + r21 * in.by + r22 * in.bz : r02 * in.bx + r12 * in.by + r22 * in.bz;
         const L tx = -(ma * (d2s + h2s) * gx), ty = -(ma * (w2s + h2s) * gy), tz = -(ma * (w2s + d2s) * gz);
         t.tam[0] = r00 * tx + r01 * ty + r02 * tz;
         t.tam[1] = r10 * tx + r11 * ty + r12 * tz;

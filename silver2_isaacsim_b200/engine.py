@@ -157,6 +157,10 @@ class HydroEngine:
         code = {"auto": L.H2O_KERNEL_AUTO, "tile": L.H2O_KERNEL_TILE, "direct": L.H2O_KERNEL_DIRECT}[choice]
         L.check(self._lib.h2o_set_kernel(self._h, code))
 
+    def set_warp_compat(self, enable: bool = True):
+        """``components`` reproduces the deviations of the reference's Warp twin."""
+        L.check(self._lib.h2o_set_warp_compat(self._h, int(bool(enable))))
+
     def set_tile_config(self, cfg: int = 0):
         """Tuning knob: tile-kernel variant (0 = default)."""
         L.check(self._lib.h2o_set_tile_config(self._h, int(cfg)))

@@ -29,7 +29,7 @@ class _WrapperBase:
     def __init__(self, width, depth, height, linear_drag_coefficient, angular_drag_coefficient,
                  linear_damping, angular_damping, water_density, gravity, linear_mass_coeff,
                  angular_mass_coeff, lift_coefficient, device="cuda:0", dtype=torch.float32,
-                 mass: float = 1.0, strict_reference_errors: bool = False):
+                 mass: float = 1.0, strict_reference_errors: bool = False, warp_compat: bool = False):
         # attribute names of numba_hydrodynamics_wrapper.py:12-24
         self.width, self.depth, self.height = width, depth, height
         self.total_volume = width * depth * height
@@ -42,6 +42,7 @@ class _WrapperBase:
         self.device = device
         self.mass = mass
         self.strict_reference_errors = strict_reference_errors
+        self.warp_compat = warp_compat  # reproduce the Warp twin's deviations
         self._dtype = dtype
         self._ctor = [width, depth, height, linear_drag_coefficient, angular_drag_coefficient,
                       linear_damping, angular_damping, water_density, gravity, linear_mass_coeff,
@@ -53,6 +54,7 @@ class _WrapperBase:
         if e is None:
             e = HydroEngine(n, dtype=self._dtype, device=self.device)
             e.set_params_uniform(self._ctor, self.mass)
+            e.set_warp_compat(self.warp_compat)
             self._engines[n] = e
         return e
 

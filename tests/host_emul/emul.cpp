@@ -40,6 +40,7 @@ static void run(int64_t n, const double* pos, const double* quat, const double* 
         in.k_damp = L(S(c[5])); in.k_damp_ang = L(S(c[6]));
         in.c_am = L(S(c[7])); in.c_am_ang = L(S(c[8])); in.c_lift = L(S(c[9]));
         in.rho_h = H(rho); in.grav_h = H(g); in.rho = L(rho);
+        in.warp_compat = false;
         Terms<H, L> t;
         L f[3], tq[3];
         bool clamped;

@@ -387,3 +387,33 @@ def test_degenerate_inputs_stay_finite(dev):
     assert s["bodies"] == n and s["nonfinite_bodies"] == 1   # ... and is counted
     assert s["still_wet_bodies"] >= 5          # wet and at rest: where the reference raises TypeError
     assert (F[2].abs() <= 1e-5).all()          # zero mass: clamp scale = 0 * 500 / |F|
+
+
+def test_warp_compat_components(golden, oracle, dev):
+    """f3: the components entry point can reproduce the Warp twin's deviations (forward rotation of
+    the accelerations, cob = cop = p when dry); the default stays Numba semantics."""
+    from silver2_isaacsim_b200 import WarpHydrodynamicsWrapper
+
+    d = golden["c2"]
+    n = 512
+    ctor = d["ctor"][0]
+    sel = np.arange(n)
+    state = {k: d[k][sel] for k in ("pos", "quat", "v", "w", "a", "al")}
+    state["pos"][:8, 2] = 5.0  # a few dry bodies
+    try:
+        oracle.set_warp_compat(True)
+        ref = oracle.components(ctor, *[state[k] for k in ("pos", "quat", "v", "w", "a", "al")])
+    finally:
+        oracle.set_warp_compat(False)
+    num = oracle.components(ctor, *[state[k] for k in ("pos", "quat", "v", "w", "a", "al")])
+    assert np.abs(ref["added_mass_force"] - num["added_mass_force"]).max() > 1e-3   # the modes do differ
+    w = WarpHydrodynamicsWrapper(*ctor, device="cuda:0", warp_compat=True)
+    t = lambda k: torch.as_tensor(state[k], dtype=torch.float32, device=dev)
+    out = w.calculate_hydrodynamic_forces(t("pos"), t("quat"), t("v"), t("w"), t("a"), t("al"))
+    for k, name in enumerate(NAMES):
+        assert scoring.fp32_ok(out[k].cpu().numpy(), ref[name], rel=2e-5).all(), name
+    assert np.allclose(out[6].cpu().numpy()[:8], state["pos"][:8], rtol=1e-6)       # dry: cob = p
+    w0 = WarpHydrodynamicsWrapper(*ctor, device="cuda:0")                            # default: Numba semantics
+    out0 = w0.calculate_hydrodynamic_forces(t("pos"), t("quat"), t("v"), t("w"), t("a"), t("al"))
+    assert scoring.fp32_ok(out0[4].cpu().numpy(), num["added_mass_force"], rel=2e-5).all()
+    assert (out0[6].cpu().numpy()[:8] == 0).all()
