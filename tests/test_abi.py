@@ -62,3 +62,28 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "hydro_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
+
+
+def test_headers_are_plain_c_and_link(built_lib, tmp_path):
+    """include/*.h compile as C99 and the example C host links against the library."""
+    import subprocess
+    from silver2_isaacsim_b200 import _lib
+    inc = os.path.join(ROOT, "include")
+    for hdr in ("h2o.h", "h2o_dlpack.h"):
+        src = tmp_path / (hdr + ".c")
+        src.write_text(f'#include "{hdr}"\nint main(void) {{ return (int)sizeof(h2o_handle) == 0; }}\n')
+        subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", inc, "-fsyntax-only", str(src)],
+                       check=True)
+    exe = tmp_path / "c_host"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-I", inc, os.path.join(ROOT, "examples", "c_host.c"), "-L", libdir,
+                    "-lh2o_b200", "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath," + libdir,
+                    "-Wl,-rpath,/usr/local/cuda/lib64", "-o", str(exe)], check=True)
+    res = subprocess.run([str(exe)], capture_output=True, text=True)
+    import torch
+    if torch.cuda.is_available():
+        assert res.returncode == 0 and "7038.67" in res.stdout and "F[0] = (" in res.stdout
+        val = float(res.stdout.split("F[0] = (")[1].split(",")[2].split(")")[0])
+        assert abs(val - 7038.675) < 0.01
+    else:
+        assert res.returncode == 1 and "no CPU path" in res.stderr  # fails loudly without a GPU
