@@ -417,3 +417,28 @@ def test_warp_compat_components(golden, oracle, dev):
     out0 = w0.calculate_hydrodynamic_forces(t("pos"), t("quat"), t("v"), t("w"), t("a"), t("al"))
     assert scoring.fp32_ok(out0[4].cpu().numpy(), num["added_mass_force"], rel=2e-5).all()
     assert (out0[6].cpu().numpy()[:8] == 0).all()
+
+
+@pytest.mark.parametrize("n_robots", [1, 7, 8, 9, 2000, 2003])
+def test_no_out_of_bounds_writes(oracle, dev, n_robots):
+    """Outputs live inside larger buffers with sentinel guards on both sides; tile tails, partial
+    robots-per-tile and the direct-kernel remainder must not write a byte outside their rows
+    (compute-sanitizer is not available on this pool, so the guards are the bounds check)."""
+    wl = W.hexapod_envs(n_robots, seed=123 + n_robots)
+    n, R, G = wl.n, n_robots, 64
+    ref = _ref(oracle, wl)
+    for kernel in ("tile", "direct"):
+        e = _engine(wl, torch.float32, dev, kernel)
+        e.set_prev(_t(wl.prev_lin, torch.float32, dev), _t(wl.prev_ang, torch.float32, dev))
+        bufF = torch.full((n + 2 * G, 3), 777.0, device=dev)
+        bufT = torch.full((n + 2 * G, 3), 777.0, device=dev)
+        bufW = torch.full((R + 2 * G, 6), 777.0, device=dev)
+        F, T, Wr = bufF[G:G + n], bufT[G:G + n], bufW[G:G + R]
+        e.step(_t(wl.pos, torch.float32, dev), _t(wl.quat_xyzw, torch.float32, dev), _t(wl.lin_vel, torch.float32, dev),
+               _t(wl.ang_vel, torch.float32, dev), wl.dt, out_force=F, out_torque=T, out_robot_wrench=Wr)
+        torch.cuda.synchronize()
+        for buf, rows in ((bufF, n), (bufT, n), (bufW, R)):
+            assert (buf[:G] == 777.0).all() and (buf[G + rows:] == 777.0).all(), (kernel, n_robots)
+        assert not (F == 777.0).all(dim=1).any() and not (Wr == 777.0).all(dim=1).any()  # every row written
+        scoring.assert_fp32(F.cpu().numpy(), ref.force, "guarded force", min_pass=0.999)
+        scoring.assert_fp32(T.cpu().numpy(), ref.torque, "guarded torque", min_pass=0.999)
