@@ -179,8 +179,9 @@ H2O_API int h2o_components(h2o_handle h, const void* pos, const void* quat, cons
 
 /* ---- host-buffer convenience path ------------------------------------------------------
  * Numba-wrapper style call with HOST arrays (the reference's CPU flavour takes and returns
- * NumPy arrays): chunked, double-buffered H2D -> step -> D2H on internal streams; returns
- * after the results are in the host buffers. */
+ * NumPy arrays): chunked, double-buffered H2D -> step -> D2H on internal streams.  Synchronous:
+ * waits for previously queued device work on entry and returns after the results are in the
+ * host buffers. */
 H2O_API int h2o_step_host(h2o_handle h, const void* pos, const void* quat, const void* lin_vel,
                           const void* ang_vel, double dt, void* out_force, void* out_torque,
                           void* out_robot_wrench);

@@ -938,6 +938,9 @@ int h2o_step_host(h2o_handle h, const void* pos, const void* quat, const void* l
     if (!(dt > 1e-6)) return H2O_OK;
     DeviceGuard g(e->device);
     if (int rc = hp_init(e)) return rc;
+    // The pipeline runs on engine-owned non-blocking streams and no caller stream is passed in:
+    // order it after whatever the caller queued before (h2o_set_prev, a previous h2o_step, ...).
+    CUDA_TRY(cudaDeviceSynchronize());
     const size_t per_in[4] = {3, 4, 3, 3};
     const size_t per_out[3] = {3, 3, 6};
 
