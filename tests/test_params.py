@@ -60,3 +60,21 @@ def test_workloads_are_seeded_and_shaped():
     e = W.uniform_small_batch()
     assert e.n == 1024 and e.table.shape == (1, 11)
     assert W.readme_buoy().meta["steps"] == 10000
+
+
+def test_trace_and_rtf_utilities(tmp_path):
+    """CSV column order of the reference's LogVelocity and the RTF arithmetic of BenchmarkRtf."""
+    import csv
+    from silver2_isaacsim_b200.trace import LOG_HEADER, RtfMeter, VelocityTrace
+
+    path = tmp_path / "velocity_log.csv"
+    tr = VelocityTrace(str(path))
+    tr.sample(np.array([[1.0, 2.0, 3.0]]), np.array([[4.0, 5.0, 6.0]]), np.array([[7.0, 8.0, 9.0]]), timestamp="t0")
+    rows = list(csv.reader(open(path)))
+    assert rows[0] == LOG_HEADER and rows[0][1:4] == ["z_position", "linear_velocity_z", "angular_velocity_z"]
+    assert rows[1] == ["t0", "3.0", "6.0", "9.0", "1.0", "4.0", "7.0", "2.0", "5.0", "8.0"]
+    lines = []
+    m = RtfMeter(report_every=600, printer=lines.append)
+    m.on_physics_step(1 / 120, n_steps=1200)
+    r = m.report()
+    assert r["steps"] == 1200 and abs(r["sim_time_s"] - 10.0) < 1e-9 and r["rtf"] > 0 and len(lines) == 1
