@@ -310,7 +310,7 @@ struct TileSmem {
     static constexpr size_t OUT_BYTES = size_t(TL::E_OUT) * kThreads * sizeof(S);
     static constexpr size_t TABLE_BYTES =
         (kParam == PARAM_TABLE) ? (size_t(MAX_TABLE_TYPES) * N_COEFF * sizeof(S) + MAX_TABLE_SLOTS) : 0;
-    static constexpr size_t ROBOT_BYTES = size_t(kThreads) * 3 * sizeof(S);  // transferred torques, [3][tile]
+    static constexpr size_t ROBOT_BYTES = size_t(kThreads) * 6 * sizeof(S);  // [3][tile] transferred torques + [3][tile] arms
     static constexpr size_t BAR_BYTES = 16 * sizeof(uint64_t);
     static constexpr size_t OFF_IN = 0;
     static constexpr size_t OFF_OUT = OFF_IN + kStagesIn * IN_BYTES;
@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
 
         RawBody<S> r;
         S cl[N_COEFF];
-        S basex = S(0), basey = S(0), basez = S(0);
+        S* const arm_scratch = robot_acc + 3 * kThreads;  // (p_i - p_base), parked across the arithmetic
         if (active) {
             load_raw<S, kLayout>(bp, tid, r);
             const S* c;
@@ -443,8 +443,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
 #pragma unroll
             for (int k = 0; k < N_COEFF; ++k) cl[k] = c[k];
             if (kRobot) {
+                // arm to the robot's slot-0 body; goes through shared memory instead of living in
+                // three registers across the whole model (register budget for 5 CTAs/SM)
                 const S* pb = bp.pos + TL::E_POS * ((tid / bpr) * bpr);
-                basex = pb[0]; basey = pb[1]; basez = pb[2];
+                arm_scratch[0 * kThreads + tid] = r.px - pb[0];
+                arm_scratch[1 * kThreads + tid] = r.py - pb[1];
+                arm_scratch[2 * kThreads + tid] = r.pz - pb[2];
             }
         }
         // the bulk store that last used this output stage must have finished reading it
@@ -479,7 +483,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
         if (kRobot && active) {
             // torque of body i about the robot's slot-0 body: tau_i + (p_i - p_base) x F_i, parked in
             // shared memory ([component][body]) next to the forces already sitting in the output stage
-            const S ax = r.px - basex, ay = r.py - basey, az = r.pz - basez;
+            const S ax = arm_scratch[0 * kThreads + tid], ay = arm_scratch[1 * kThreads + tid],
+                    az = arm_scratch[2 * kThreads + tid];
             robot_acc[0 * TB + tid] = T[0] + (ay * F[2] - az * F[1]);
             robot_acc[1 * TB + tid] = T[1] + (az * F[0] - ax * F[2]);
             robot_acc[2 * TB + tid] = T[2] + (ax * F[1] - ay * F[0]);
