@@ -33,6 +33,27 @@ BYTES_PER_BODY_F32 = 168  # 19 state reads + 11 coefficient reads + 12 writes, f
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
 
 
+_STDOUT_FD = None
+
+
+def claim_stdout():
+    """Libraries (NCCL prints its version banner) write to fd 1; the contract is ONE JSON line on
+    stdout.  Keep a private handle on the real stdout and point fd 1 at stderr for everything else."""
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _STDOUT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_STDOUT_FD, data)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -197,7 +218,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------
@@ -462,7 +483,7 @@ def run_b200(args):
             "e2e": e2e, "gpu_launches": int(launches * world), "clocks": clocks,
             "cpu_baseline": cpu, "global_stats": gstats, "extra": extra,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         import torch.distributed as dist
 
@@ -472,6 +493,7 @@ def run_b200(args):
 
 def main():
     args = parse()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
