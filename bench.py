@@ -141,6 +141,26 @@ class ClockSampler(threading.Thread):
                 "samples": len(under)}
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this rank's CPU threads (and hence its first-touched pinned buffers) to the NUMA node of
+    its GPU; with 8 ranks on one box the host side of the e2e path otherwise crosses sockets."""
+    try:
+        import pynvml as nv
+
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = nv.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def physical_gpu_index(local_rank):
     vis = os.environ.get("CUDA_VISIBLE_DEVICES")
     if vis:
@@ -377,6 +397,8 @@ def run_b200(args):
         raise SystemExit("bench.py (b200 arm) needs a GPU: the engine has no CPU path")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    if world > 1:
+        bind_to_gpu_numa_node(physical_gpu_index(local))
     dtype = torch.float32 if args.dtype == "f32" else torch.float64
     n = args.bodies_per_gpu
     bpb = BYTES_PER_BODY_F32 * (1 if dtype == torch.float32 else 2)
