@@ -284,6 +284,14 @@ def time_steps(torch, sharding, batches, steps, dt, dev, use_graph=True):
         graph.replay()  # one untimed replay
     n_rep = steps // per if per else 0
     rem = steps - n_rep * per
+    rem_graph = None
+    if graph is not None and rem >= 2:
+        # the steps that do not fill a whole graph get their own (shorter) graph
+        rem_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(rem_graph, stream=side):
+            for i in range(rem):
+                batches[(n_rep * per + i) % nb][0].step_bound(dt)
+        rem_graph.replay()
     torch.cuda.synchronize(dev)
     sharding.barrier()
     torch.cuda.synchronize(dev)
@@ -291,14 +299,21 @@ def time_steps(torch, sharding, batches, steps, dt, dev, use_graph=True):
     ev0.record()
     for _ in range(n_rep):
         graph.replay()
-    for i in range(rem):
-        batches[i % nb][0].step_bound(dt)
+    if rem_graph is not None:
+        rem_graph.replay()
+    else:
+        for i in range(rem):
+            batches[i % nb][0].step_bound(dt)
     ev1.record()
     torch.cuda.synchronize(dev)
     w1 = time.perf_counter()
     sharding.barrier()
     ms = ev0.elapsed_time(ev1)
-    return ms, steps, (w0, w1), (f"CUDA graph replay ({per} steps per graph) + {rem} eager" if per else "eager launches")
+    mode = "eager launches"
+    if per:
+        mode = f"CUDA graph replay ({n_rep} x {per} steps" + (f" + 1 x {rem} steps)" if rem_graph is not None else
+                                                               f") + {rem} eager")
+    return ms, steps, (w0, w1), mode
 
 
 def side_measurements(torch, W, dev, dtype_main):
