@@ -82,6 +82,11 @@ H2O_API int h2o_destroy(h2o_handle h);
 /* waterDensity, gravity (hydrodynamics_behavior.py:30-31; hydrodynamics_config.json "globals") */
 H2O_API int h2o_set_globals(h2o_handle h, double water_density, double gravity);
 
+/* Generalisation the reference's signatures admit but its scenes never use:
+ * a uniform water current (drag, damping and lift then see v - current) and the height of the flat
+ * water surface (the reference's is the plane z = 0).  NULL / 0 = the reference's behaviour. */
+H2O_API int h2o_set_environment(h2o_handle h, const double current_xyz[3], double surface_z);
+
 /* Same twelve scalars, same order as the reference wrapper ctor
  * (numba_hydrodynamics_wrapper.py:9-10): width, depth, height, linear_drag_coefficient,
  * angular_drag_coefficient, linear_damping, angular_damping, water_density, gravity,

@@ -47,6 +47,7 @@ SIGNATURES = {
     "h2o_create": (c_int, [POINTER(c_void_p), c_int64, c_int, c_int]),
     "h2o_destroy": (c_int, [_P]),
     "h2o_set_globals": (c_int, [_P, c_double, c_double]),
+    "h2o_set_environment": (c_int, [_P, POINTER(c_double), c_double]),
     "h2o_set_params_uniform": (c_int, [_P, POINTER(c_double), c_double]),
     "h2o_set_part_table": (c_int, [_P, c_int, POINTER(c_double), c_int, POINTER(c_int32)]),
     "h2o_set_params_per_body": (c_int, [_P, _P, c_int, _P]),

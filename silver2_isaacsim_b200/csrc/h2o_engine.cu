@@ -54,6 +54,8 @@ struct h2o_engine {
     int64_t n = 0;
     size_t esz = 4;
     double rho = 1025.0, grav = 9.81;
+    double current[3] = {0.0, 0.0, 0.0};  // uniform water current
+    double surface_z = 0.0;               // flat water surface height
     int param_mode = -1;  // -1 unset, PARAM_TABLE, PARAM_PER_BODY
     void* coeff = nullptr;
     int64_t coeff_rows = 0;
@@ -379,6 +381,8 @@ static int step_device(h2o_engine* e, int layout, const void* pos, const void* q
     a.bodies_per_robot = e->bodies_per_robot;
     a.quat_wxyz = e->quat_order == H2O_QUAT_WXYZ;
     a.rho = e->rho; a.grav = e->grav; a.inv_dt = 1.0 / dt;
+    for (int k = 0; k < 3; ++k) a.current[k] = e->current[k];
+    a.surface_z = e->surface_z;
     return e->dtype == H2O_F32 ? step_typed<float>(e, layout, a, stream) : step_typed<double>(e, layout, a, stream);
 }
 
@@ -479,6 +483,15 @@ int h2o_set_globals(h2o_handle h, double water_density, double gravity)
     if (!e) return H2O_ERR_BAD_HANDLE;
     e->rho = water_density;
     e->grav = gravity;
+    return H2O_OK;
+}
+
+int h2o_set_environment(h2o_handle h, const double current_xyz[3], double surface_z)
+{
+    h2o_engine* e = check(h);
+    if (!e) return H2O_ERR_BAD_HANDLE;
+    for (int k = 0; k < 3; ++k) e->current[k] = current_xyz ? current_xyz[k] : 0.0;
+    e->surface_z = surface_z;
     return H2O_OK;
 }
 
@@ -893,6 +906,8 @@ int h2o_components(h2o_handle h, const void* pos, const void* quat, const void* 
     a.quat_wxyz = e->quat_order == H2O_QUAT_WXYZ;
     a.warp_compat = e->warp_compat;
     a.rho = e->rho; a.grav = e->grav;
+    for (int k = 0; k < 3; ++k) a.current[k] = e->current[k];
+    a.surface_z = e->surface_z;
     const int grid = int((e->n + 255) / 256);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (e->dtype == H2O_F32) components_kernel<float><<<grid, 256, 0, s>>>(a);

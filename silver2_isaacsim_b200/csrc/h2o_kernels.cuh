@@ -58,6 +58,8 @@ struct StepArgs {
     int bodies_per_robot;    // 0 = no articulation
     int quat_wxyz;           // 1: incoming quaternions are wxyz (Isaac core), else xyzw
     double rho, grav, inv_dt;
+    double current[3];       // uniform water current (world): the flow-relative velocity is v - current
+    double surface_z;        // height of the (flat) water surface; the reference's is z = 0
 };
 
 // ---------------------------------------------------------------------------
@@ -187,17 +189,25 @@ __device__ __forceinline__ void load_raw(const BodyPtrs<S>& p, long long i, RawB
 
 // Assemble the model input: quaternion order (hydrodynamics_behavior.py:194),
 // finite-difference acceleration (hydrodynamics_behavior.py:196-202), coefficients.
+// Environment generalisation: uniform current and surface height; both zero
+// reproduces the reference exactly (x - 0 is exact).
+struct Env {
+    double cx, cy, cz, surface_z;
+};
+
 template <typename S>
 __device__ __forceinline__ void make_body_in(const RawBody<S>& r, const S* c, int quat_wxyz, double rho,
-                                             double grav, S inv_dt, BodyIn<double, S>& in)
+                                             double grav, S inv_dt, const Env& env, BodyIn<double, S>& in)
 {
-    in.pz = double(r.pz);
+    in.pz = double(r.pz) - env.surface_z;
     if (quat_wxyz) {
         in.qx = double(r.q1); in.qy = double(r.q2); in.qz = double(r.q3); in.qw = double(r.q0);
     } else {
         in.qx = double(r.q0); in.qy = double(r.q1); in.qz = double(r.q2); in.qw = double(r.q3);
     }
-    in.vx = r.vx; in.vy = r.vy; in.vz = r.vz;
+    // drag, damping and lift see the flow-relative velocity; accelerations are differences of
+    // body velocities and do not change under a steady current
+    in.vx = r.vx - S(env.cx); in.vy = r.vy - S(env.cy); in.vz = r.vz - S(env.cz);
     in.wx = r.wx; in.wy = r.wy; in.wz = r.wz;
     if (sizeof(S) == 4) {  // fp32 fast path folds 1/dt into the added-mass constants
         in.ax = r.vx - r.pvx; in.ay = r.vy - r.pvy; in.az = r.vz - r.pvz;
@@ -402,6 +412,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
 
     ThreadStats st;
     const S inv_dt = S(a.inv_dt);
+    const Env env{a.current[0], a.current[1], a.current[2], a.surface_z};
     const int bpr = a.bodies_per_robot;
 
     long long next_begin = first_begin;
@@ -465,7 +476,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
                 T[0] = r.q0 + cl[9]; T[1] = r.q1 + r.q2 + r.pvx + r.pvz; T[2] = r.q3 + cl[10] + r.pwy;
             } else {
                 BodyIn<double, S> bin;
-                make_body_in<S>(r, cl, a.quat_wxyz, a.rho, a.grav, inv_dt, bin);
+                make_body_in<S>(r, cl, a.quat_wxyz, a.rho, a.grav, inv_dt, env, bin);
                 body_step<S>(bin, cl[10], F, T, kStats ? &st : nullptr);
             }
 
@@ -562,7 +573,7 @@ __global__ void __launch_bounds__(256) step_direct_kernel(const __grid_constant_
             for (int k = 0; k < N_COEFF; ++k) cl[k] = c[k];
         }
         BodyIn<double, S> bin;
-        make_body_in<S>(r, cl, a.quat_wxyz, a.rho, a.grav, S(a.inv_dt), bin);
+        make_body_in<S>(r, cl, a.quat_wxyz, a.rho, a.grav, S(a.inv_dt), Env{a.current[0], a.current[1], a.current[2], a.surface_z}, bin);
         S F[3], T[3];
         body_step<S>(bin, cl[10], F, T, kStats ? &st : nullptr);
         S* of = reinterpret_cast<S*>(a.out_force) + 3 * i;
@@ -631,6 +642,7 @@ struct ComponentsArgs {
     int n_slots, n_types, param_mode, quat_wxyz;
     int warp_compat;  // reproduce the deviations of the reference's Warp twin
     double rho, grav;
+    double current[3], surface_z;
 };
 
 template <typename S>
@@ -654,7 +666,7 @@ __global__ void __launch_bounds__(256) components_kernel(const __grid_constant__
     r.wx = w[0]; r.wy = w[1]; r.wz = w[2];
     r.pvx = r.vx; r.pvy = r.vy; r.pvz = r.vz; r.pwx = r.wx; r.pwy = r.wy; r.pwz = r.wz;
     BodyIn<double, S> in;
-    make_body_in<S>(r, c, a.quat_wxyz, a.rho, a.grav, S(0), in);
+    make_body_in<S>(r, c, a.quat_wxyz, a.rho, a.grav, S(0), Env{a.current[0], a.current[1], a.current[2], a.surface_z}, in);
     in.ax = la[0]; in.ay = la[1]; in.az = la[2];
     in.bx = aa[0]; in.by = aa[1]; in.bz = aa[2];
     in.acc_scale = S(1);

@@ -104,6 +104,12 @@ class HydroEngine:
         L.check(self._lib.h2o_set_quat_order(self._h, L.H2O_QUAT_WXYZ if order == "wxyz" else L.H2O_QUAT_XYZW))
         self._quat_order = order
 
+    def set_environment(self, current=(0.0, 0.0, 0.0), surface_z: float = 0.0):
+        """Uniform water current (world frame) and height of the flat water surface; the defaults are
+        the reference's still water with its surface at z = 0."""
+        arr = (ctypes.c_double * 3)(*[float(x) for x in current])
+        L.check(self._lib.h2o_set_environment(self._h, arr, float(surface_z)))
+
     def set_params_uniform(self, ctor12: Sequence[float], mass: float):
         """Same twelve scalars, same order, as the reference wrapper ctor
         (numba_hydrodynamics_wrapper.py:9-10) + the body mass used by the clamp."""

@@ -442,3 +442,30 @@ def test_no_out_of_bounds_writes(oracle, dev, n_robots):
         assert not (F == 777.0).all(dim=1).any() and not (Wr == 777.0).all(dim=1).any()  # every row written
         scoring.assert_fp32(F.cpu().numpy(), ref.force, "guarded force", min_pass=0.999)
         scoring.assert_fp32(T.cpu().numpy(), ref.torque, "guarded torque", min_pass=0.999)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["fp32", "fp64"])
+def test_environment_current_and_surface_height(oracle, dev, dtype):
+    """f4: a uniform current and a raised water surface equal the reference model evaluated with the
+    flow-relative velocity and the surface-relative height (accelerations and v_prev unchanged)."""
+    wl = W.heterogeneous_boxes(60_000, seed=99)
+    cur, eta = np.array([0.4, -0.25, 0.1]), 0.35
+    cur = cur.astype(np.float32).astype(np.float64)
+    e = _engine(wl, dtype, dev, "tile")
+    e.set_environment(current=cur, surface_z=eta)
+    F, T = _run_step(e, wl, dtype, dev)
+    pos = wl.pos.astype(np.float64) - np.array([0, 0, eta])
+    if dtype == torch.float32:  # what the kernel sees: fp32 velocity difference, fp64 height difference
+        vrel = (wl.lin_vel - cur.astype(np.float32)).astype(np.float64)
+        prel = (wl.prev_lin.astype(np.float64) - wl.lin_vel.astype(np.float64)) + vrel
+    else:
+        vrel = wl.lin_vel.astype(np.float64) - cur
+        prel = wl.prev_lin.astype(np.float64) - cur
+    ref = oracle.step(wl.ctor_rows(), wl.masses(), pos, wl.quat_xyzw, vrel, wl.ang_vel, prel, wl.prev_ang, wl.dt)
+    wl2 = W.Workload(**{**wl.__dict__, "pos": pos})
+    _check(wl2, dtype, ref, F, T, "environment")
+    prev = e.prev_velocities().double().cpu().numpy()
+    assert (prev[:, :3] == wl.lin_vel.astype(np.float64)).all()   # the carried state stays the BODY velocity
+    e.set_environment()                                           # back to still water at z = 0
+    F0, T0 = _run_step(e, wl, dtype, dev)
+    _check(wl, dtype, _ref(oracle, wl), F0, T0, "environment reset")
