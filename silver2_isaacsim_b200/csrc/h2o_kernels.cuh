@@ -7,7 +7,7 @@
 //   -> solve_hydrodynamics                  numba_hydrodynamics.py:255-314
 // (one `dim=1` Warp launch + 6 staging copies + ~30 torch micro-kernels per body).
 //
-// Two kernels share the per-body arithmetic of h2o_model.cuh:
+// The kernels share the per-body arithmetic of h2o_model.cuh:
 //
 //   step_tile_kernel   persistent CTAs; every input array of a tile of bodies is
 //                      brought into shared memory by the TMA engine
@@ -18,8 +18,11 @@
 //                      no uncoalesced or partial-sector traffic.  Optional
 //                      per-robot wrench summed out of shared memory.
 //   step_direct_kernel one thread per body, plain global loads; used for small
-//                      batches (latency-bound), unaligned pointers and the
-//                      full-signature `components` entry point.
+//                      batches (latency-bound), unaligned pointers and tile tails.
+//   components_kernel  batched solve_hydrodynamics in the reference's full signature
+//                      (eight vectors + sub_ratio), optional Warp-twin compatibility.
+//   robot_wrench_kernel  one warp per robot, shuffle reduction (tails, big robots).
+//   free_body_kernel   harness stepper for stand-alone rollouts.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -310,7 +313,6 @@ template <typename S, int kLayout, int kParam> struct TileLayout {
     static constexpr int E_COEFF = (kParam == PARAM_PER_BODY) ? N_COEFF : 0;
     static constexpr int E_IN = E_POS + E_QUAT + E_LIN + E_ANG + E_PREV + E_COEFF;
     static constexpr int E_OUT = 3 + 3 + 6;  // force, torque, prev
-    static constexpr int E_IN_ALL = E_IN;
 };
 
 template <typename S, int kLayout, int kParam, int kThreads, int kStagesIn, int kStagesOut>
