@@ -469,3 +469,30 @@ def test_environment_current_and_surface_height(oracle, dev, dtype):
     e.set_environment()                                           # back to still water at z = 0
     F0, T0 = _run_step(e, wl, dtype, dev)
     _check(wl, dtype, _ref(oracle, wl), F0, T0, "environment reset")
+
+
+def test_integration_md_raw_ctypes_snippet(dev):
+    """The raw C-ABI binding shown in INTEGRATION.md section 3 (no helper layer) works as written."""
+    import ctypes
+    from silver2_isaacsim_b200 import _lib
+
+    n = 4096
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    lib.h2o_last_error.restype = ctypes.c_char_p
+    h = ctypes.c_void_p()
+    assert lib.h2o_create(ctypes.byref(h), ctypes.c_int64(n), 0, 0) == 0
+    ctor = (ctypes.c_double * 12)(1, 1, 1, 1.2, 0.8, 300, 150, 1025, 9.81, 0.05, 0.02, 1.0)
+    assert lib.h2o_set_params_uniform(h, ctor, ctypes.c_double(512.5)) == 0
+    pos = torch.zeros(n, 3, device=dev); pos[:, 2] = -0.2
+    quat_xyzw = torch.zeros(n, 4, device=dev); quat_xyzw[:, 3] = 1
+    lin_vel = torch.zeros(n, 3, device=dev); lin_vel[:, 0] = 0.1; lin_vel[:, 2] = -0.3
+    ang_vel = torch.zeros(n, 3, device=dev)
+    out_force, out_torque = torch.empty(n, 3, device=dev), torch.empty(n, 3, device=dev)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    rc = lib.h2o_step(h, p(pos), p(quat_xyzw), p(lin_vel), p(ang_vel), ctypes.c_double(1 / 60),
+                      p(out_force), p(out_torque), None, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, lib.h2o_last_error()
+    torch.cuda.synchronize()
+    # SURVEY.md Appendix B GV1 buoyancy + drag (first step: v_prev = 0 -> added mass acts as well)
+    assert abs(float(out_force[0, 2]) - (7038.675 + 75.915 + 2.1525 + 0.7 * 51.25 * 0.3 * 60)) < 0.05
+    assert lib.h2o_destroy(h) == 0
