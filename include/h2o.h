@@ -146,8 +146,15 @@ H2O_API int h2o_step_physx(h2o_handle h, const void* transforms, const void* vel
                            void* out_force, void* out_torque, void* out_robot_wrench,
                            h2o_stream stream);
 
-/* Bind the tensors once, then step with a single cheap call (layout: 0 split, 1 physx;
- * for physx pass transforms as pos, velocities as lin_vel, quat = ang_vel = NULL). */
+/* Same, RigidPrimView layout: pos (N,3), quat (N,4) from get_world_poses and the fused
+ * velocities (N,6) = [v, w] from get_velocities (hydrodynamics_behavior.py:178-189) -- no slicing
+ * copies on the caller's side. */
+H2O_API int h2o_step_view(h2o_handle h, const void* pos, const void* quat, const void* velocities, double dt,
+                          void* out_force, void* out_torque, void* out_robot_wrench, h2o_stream stream);
+
+/* Bind the tensors once, then step with a single cheap call (layout: 0 split, 1 physx, 2 view;
+ * physx: pass transforms as pos, velocities as lin_vel, quat = ang_vel = NULL;
+ * view: pass velocities as lin_vel, ang_vel = NULL). */
 H2O_API int h2o_bind(h2o_handle h, int layout, const void* pos, const void* quat, const void* lin_vel,
                      const void* ang_vel, void* out_force, void* out_torque, void* out_robot_wrench);
 H2O_API int h2o_unbind(h2o_handle h);

@@ -69,6 +69,9 @@ H2O_API int h2o_step_dl(h2o_handle h, const DLTensor* pos, const DLTensor* quat,
 H2O_API int h2o_step_physx_dl(h2o_handle h, const DLTensor* transforms, const DLTensor* velocities,
                               double dt, const DLTensor* out_force, const DLTensor* out_torque,
                               const DLTensor* out_robot_wrench, h2o_stream stream);
+H2O_API int h2o_step_view_dl(h2o_handle h, const DLTensor* pos, const DLTensor* quat, const DLTensor* velocities,
+                             double dt, const DLTensor* out_force, const DLTensor* out_torque,
+                             const DLTensor* out_robot_wrench, h2o_stream stream);
 H2O_API int h2o_bind_dl(h2o_handle h, int layout, const DLTensor* pos, const DLTensor* quat,
                         const DLTensor* lin_vel, const DLTensor* ang_vel, const DLTensor* out_force,
                         const DLTensor* out_torque, const DLTensor* out_robot_wrench);

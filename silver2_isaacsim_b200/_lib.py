@@ -23,7 +23,7 @@ STATUS_NAMES = {
 H2O_F32, H2O_F64 = 0, 1
 H2O_QUAT_XYZW, H2O_QUAT_WXYZ = 0, 1
 H2O_KERNEL_AUTO, H2O_KERNEL_TILE, H2O_KERNEL_DIRECT = 0, 1, 2
-LAYOUT_SPLIT, LAYOUT_PHYSX = 0, 1
+LAYOUT_SPLIT, LAYOUT_PHYSX, LAYOUT_VIEW = 0, 1, 2
 N_COEFF = 11
 N_STATS = 8
 STATS_FIELDS = ("sum_force_norm", "max_force_norm", "wet_bodies", "clamped_bodies",
@@ -62,6 +62,7 @@ SIGNATURES = {
     "h2o_get_prev": (c_int, [_P, _P, _P, _P]),
     "h2o_step": (c_int, [_P, _P, _P, _P, _P, c_double, _P, _P, _P, _P]),
     "h2o_step_physx": (c_int, [_P, _P, _P, c_double, _P, _P, _P, _P]),
+    "h2o_step_view": (c_int, [_P, _P, _P, _P, c_double, _P, _P, _P, _P]),
     "h2o_bind": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P]),
     "h2o_unbind": (c_int, [_P]),
     "h2o_step_bound": (c_int, [_P, c_double, _P]),
@@ -83,6 +84,7 @@ SIGNATURES = {
     # include/h2o_dlpack.h
     "h2o_step_dl": (c_int, [_P, _P, _P, _P, _P, c_double, _P, _P, _P, _P]),
     "h2o_step_physx_dl": (c_int, [_P, _P, _P, c_double, _P, _P, _P, _P]),
+    "h2o_step_view_dl": (c_int, [_P, _P, _P, _P, c_double, _P, _P, _P, _P]),
     "h2o_bind_dl": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P]),
     "h2o_components_dl": (c_int, [_P, _P, _P, _P, _P, _P, _P, POINTER(c_void_p), _P, _P, _P]),
     "h2o_set_params_per_body_dl": (c_int, [_P, _P, _P]),

@@ -115,13 +115,12 @@ class BatchedHydrodynamicsBehavior:
             dev, dt_ = self._engine.device, self._dtype
             positions = positions.to(device=dev, dtype=dt_).contiguous()
             orientations = orientations.to(device=dev, dtype=dt_).contiguous()
-            full_velocities = full_velocities.to(device=dev, dtype=dt_)
-            linear_velocity = full_velocities[:, 0:3].contiguous()
-            angular_velocity = full_velocities[:, 3:6].contiguous()
+            full_velocities = full_velocities.to(device=dev, dtype=dt_).contiguous()
         except (UnboundLocalError, IndexError, RuntimeError, AttributeError):
             return  # the reference silently skips the step (:191-192)
-        self._engine.step(positions, orientations, linear_velocity, angular_velocity, delta_time,
-                          out_force=self._F, out_torque=self._T, out_robot_wrench=self.robot_wrench)
+        # the (N,6) velocity tensor is consumed as it is: no [:, 0:3] / [:, 3:6] slicing copies (:188-189)
+        self._engine.step_view(positions, orientations, full_velocities, delta_time,
+                               out_force=self._F, out_torque=self._T, out_robot_wrench=self.robot_wrench)
         self._view.apply_forces_and_torques_at_pos(forces=self._F, torques=self._T, positions=positions,
                                                    is_global=True)
 

@@ -271,7 +271,8 @@ static int step_typed2(h2o_engine* e, StepArgs& a, cudaStream_t stream)
     const int TB = robots ? tile_bodies_for(RobotCfgs<S>::C::kThreads, sizeof(S), a.bodies_per_robot)
                           : tile_bodies_for(DC::kThreads, sizeof(S), 0);
     bool ptr_ok = aligned16(a.pos) && aligned16(a.lin) && aligned16(a.prev) && aligned16(a.out_force) &&
-                  aligned16(a.out_torque) && (kLayout == LAYOUT_PHYSX || (aligned16(a.quat) && aligned16(a.ang))) &&
+                  aligned16(a.out_torque) && (kLayout == LAYOUT_PHYSX || aligned16(a.quat)) &&
+                  (kLayout != LAYOUT_SPLIT || aligned16(a.ang)) &&
                   (kParam == PARAM_TABLE || aligned16(a.coeff));
     bool use_tile = false;
     if (e->kernel_choice == H2O_KERNEL_TILE) use_tile = true;
@@ -348,9 +349,12 @@ static int step_typed(h2o_engine* e, int layout, StepArgs& a, cudaStream_t strea
     if (layout == LAYOUT_SPLIT) {
         if (e->param_mode == PARAM_TABLE) { H2O_DISPATCH(LAYOUT_SPLIT, PARAM_TABLE); }
         else { H2O_DISPATCH(LAYOUT_SPLIT, PARAM_PER_BODY); }
-    } else {
+    } else if (layout == LAYOUT_PHYSX) {
         if (e->param_mode == PARAM_TABLE) { H2O_DISPATCH(LAYOUT_PHYSX, PARAM_TABLE); }
         else { H2O_DISPATCH(LAYOUT_PHYSX, PARAM_PER_BODY); }
+    } else {
+        if (e->param_mode == PARAM_TABLE) { H2O_DISPATCH(LAYOUT_VIEW, PARAM_TABLE); }
+        else { H2O_DISPATCH(LAYOUT_VIEW, PARAM_PER_BODY); }
     }
 #undef H2O_DISPATCH
 }
@@ -719,15 +723,31 @@ int h2o_step_physx(h2o_handle h, const void* transforms, const void* velocities,
                        out_robot_wrench, e->n, 0, e->prev, coeff_at(e, 0), static_cast<cudaStream_t>(stream));
 }
 
+int h2o_step_view(h2o_handle h, const void* pos, const void* quat, const void* velocities, double dt,
+                  void* out_force, void* out_torque, void* out_robot_wrench, h2o_stream stream)
+{
+    h2o_engine* e = check(h);
+    if (!e) return H2O_ERR_BAD_HANDLE;
+    const void* p[5] = {pos, quat, velocities, out_force, out_torque};
+    if (int rc = check_ptrs(p, 5)) return rc;
+    DeviceGuard g(e->device);
+    return step_device(e, LAYOUT_VIEW, pos, quat, velocities, nullptr, dt, out_force, out_torque, out_robot_wrench,
+                       e->n, 0, e->prev, coeff_at(e, 0), static_cast<cudaStream_t>(stream));
+}
+
 int h2o_bind(h2o_handle h, int layout, const void* pos, const void* quat, const void* lin_vel, const void* ang_vel,
              void* out_force, void* out_torque, void* out_robot_wrench)
 {
     h2o_engine* e = check(h);
     if (!e) return H2O_ERR_BAD_HANDLE;
-    if (layout != LAYOUT_SPLIT && layout != LAYOUT_PHYSX) return fail(H2O_ERR_BAD_ARGUMENT, "bad layout %d", layout);
+    if (layout != LAYOUT_SPLIT && layout != LAYOUT_PHYSX && layout != LAYOUT_VIEW)
+        return fail(H2O_ERR_BAD_ARGUMENT, "bad layout %d", layout);
     if (layout == LAYOUT_SPLIT) {
         const void* p[6] = {pos, quat, lin_vel, ang_vel, out_force, out_torque};
         if (int rc = check_ptrs(p, 6)) return rc;
+    } else if (layout == LAYOUT_VIEW) {
+        const void* p[5] = {pos, quat, lin_vel, out_force, out_torque};
+        if (int rc = check_ptrs(p, 5)) return rc;
     } else {
         const void* p[4] = {pos, lin_vel, out_force, out_torque};
         if (int rc = check_ptrs(p, 4)) return rc;
@@ -1195,6 +1215,23 @@ int h2o_step_physx_dl(h2o_handle h, const DLTensor* transforms, const DLTensor* 
     return h2o_step_physx(h, x, v, dt, const_cast<void*>(f), const_cast<void*>(t), const_cast<void*>(rw), stream);
 }
 
+int h2o_step_view_dl(h2o_handle h, const DLTensor* pos, const DLTensor* quat, const DLTensor* velocities, double dt,
+                     const DLTensor* out_force, const DLTensor* out_torque, const DLTensor* out_robot_wrench,
+                     h2o_stream stream)
+{
+    h2o_engine* e = check(h);
+    if (!e) return H2O_ERR_BAD_HANDLE;
+    const void *p, *q, *v, *f, *t, *rw;
+    int rc;
+    if ((rc = dl_check(e, pos, "position", e->n, 3, false, &p))) return rc;
+    if ((rc = dl_check(e, quat, "orientation_quat", e->n, 4, false, &q))) return rc;
+    if ((rc = dl_check(e, velocities, "velocities", e->n, 6, false, &v))) return rc;
+    if ((rc = dl_check(e, out_force, "out_force", e->n, 3, false, &f))) return rc;
+    if ((rc = dl_check(e, out_torque, "out_torque", e->n, 3, false, &t))) return rc;
+    if ((rc = dl_wrench(e, out_robot_wrench, &rw))) return rc;
+    return h2o_step_view(h, p, q, v, dt, const_cast<void*>(f), const_cast<void*>(t), const_cast<void*>(rw), stream);
+}
+
 int h2o_bind_dl(h2o_handle h, int layout, const DLTensor* pos, const DLTensor* quat, const DLTensor* lin_vel,
                 const DLTensor* ang_vel, const DLTensor* out_force, const DLTensor* out_torque,
                 const DLTensor* out_robot_wrench)
@@ -1210,6 +1247,10 @@ int h2o_bind_dl(h2o_handle h, int layout, const DLTensor* pos, const DLTensor* q
         if ((rc = dl_check(e, ang_vel, "angular_vel", e->n, 3, false, &w))) return rc;
     } else if (layout == LAYOUT_PHYSX) {
         if ((rc = dl_check(e, pos, "transforms", e->n, 7, false, &p))) return rc;
+        if ((rc = dl_check(e, lin_vel, "velocities", e->n, 6, false, &v))) return rc;
+    } else if (layout == LAYOUT_VIEW) {
+        if ((rc = dl_check(e, pos, "position", e->n, 3, false, &p))) return rc;
+        if ((rc = dl_check(e, quat, "orientation_quat", e->n, 4, false, &q))) return rc;
         if ((rc = dl_check(e, lin_vel, "velocities", e->n, 6, false, &v))) return rc;
     } else {
         return fail(H2O_ERR_BAD_ARGUMENT, "bad layout %d", layout);

@@ -32,7 +32,7 @@
 
 namespace h2o {
 
-enum : int { LAYOUT_SPLIT = 0, LAYOUT_PHYSX = 1 };
+enum : int { LAYOUT_SPLIT = 0, LAYOUT_PHYSX = 1, LAYOUT_VIEW = 2 };
 enum : int { PARAM_TABLE = 0, PARAM_PER_BODY = 1 };
 constexpr int N_COEFF = 11;
 constexpr int MAX_TABLE_TYPES = 64;
@@ -42,6 +42,8 @@ constexpr int N_STATS = 8;  // sum|F|, max|F|, wet, clamped, nonfinite, still, b
 struct StepArgs {
     // LAYOUT_SPLIT: pos (N,3), quat (N,4), lin (N,3), ang (N,3)
     // LAYOUT_PHYSX: pos = transforms (N,7) [p, q], lin = velocities (N,6) [v, w]
+    // LAYOUT_VIEW:  pos (N,3), quat (N,4), lin = velocities (N,6) [v, w]  -- what RigidPrimView
+    //               hands out (get_world_poses + get_velocities, hydrodynamics_behavior.py:178-179)
     const void* pos;
     const void* quat;
     const void* lin;
@@ -162,7 +164,7 @@ template <typename S, int kLayout>
 __device__ __forceinline__ void load_raw(const BodyPtrs<S>& p, long long i, RawBody<S>& r)
 {
     using V2 = typename Vec2Of<S>::type;
-    if (kLayout == LAYOUT_SPLIT) {
+    if (kLayout == LAYOUT_SPLIT || kLayout == LAYOUT_VIEW) {
         const S* pp = p.pos + 3 * i;
         r.px = pp[0]; r.py = pp[1]; r.pz = pp[2];
         if (sizeof(S) == 4) {
@@ -173,10 +175,16 @@ __device__ __forceinline__ void load_raw(const BodyPtrs<S>& p, long long i, RawB
             const double2 qb = *reinterpret_cast<const double2*>(p.quat + 4 * i + 2);
             r.q0 = qa.x; r.q1 = qa.y; r.q2 = qb.x; r.q3 = qb.y;
         }
-        const S* pv = p.lin + 3 * i;
-        r.vx = pv[0]; r.vy = pv[1]; r.vz = pv[2];
-        const S* pw = p.ang + 3 * i;
-        r.wx = pw[0]; r.wy = pw[1]; r.wz = pw[2];
+        if (kLayout == LAYOUT_SPLIT) {
+            const S* pv = p.lin + 3 * i;
+            r.vx = pv[0]; r.vy = pv[1]; r.vz = pv[2];
+            const S* pw = p.ang + 3 * i;
+            r.wx = pw[0]; r.wy = pw[1]; r.wz = pw[2];
+        } else {
+            const V2* pv = reinterpret_cast<const V2*>(p.lin + 6 * i);
+            const V2 a = pv[0], b = pv[1], c = pv[2];
+            r.vx = a.x; r.vy = a.y; r.vz = b.x; r.wx = b.y; r.wy = c.x; r.wz = c.y;
+        }
     } else {
         const S* pp = p.pos + 7 * i;
         r.px = pp[0]; r.py = pp[1]; r.pz = pp[2];
@@ -305,8 +313,8 @@ __device__ __forceinline__ void flush_stats(const ThreadStats& st, double* stats
 // ---------------------------------------------------------------------------
 template <typename S, int kLayout, int kParam> struct TileLayout {
     // elements (of S) per body for each staged stream
-    static constexpr int E_POS = (kLayout == LAYOUT_SPLIT) ? 3 : 7;
-    static constexpr int E_QUAT = (kLayout == LAYOUT_SPLIT) ? 4 : 0;
+    static constexpr int E_POS = (kLayout == LAYOUT_PHYSX) ? 7 : 3;
+    static constexpr int E_QUAT = (kLayout == LAYOUT_PHYSX) ? 0 : 4;
     static constexpr int E_LIN = (kLayout == LAYOUT_SPLIT) ? 3 : 6;
     static constexpr int E_ANG = (kLayout == LAYOUT_SPLIT) ? 3 : 0;
     static constexpr int E_PREV = 6;
@@ -601,7 +609,7 @@ __global__ void __launch_bounds__(256) robot_wrench_kernel(const __grid_constant
     const int lane = threadIdx.x & 31;
     const long long n_robots = a.n / a.bodies_per_robot;
     if (robot >= n_robots) return;
-    constexpr int EP = (kLayout == LAYOUT_SPLIT) ? 3 : 7;
+    constexpr int EP = (kLayout == LAYOUT_PHYSX) ? 7 : 3;
     const S* pos = reinterpret_cast<const S*>(a.pos);
     const S* Fp = reinterpret_cast<const S*>(a.out_force);
     const S* Tp = reinterpret_cast<const S*>(a.out_torque);

@@ -241,6 +241,16 @@ class HydroEngine:
                                             dl(W), _stream_ptr(self.device)))
         return (F, T) if W is None else (F, T, W)
 
+    def step_view(self, position, orientation_quat, velocities, dt: float, out_force=None, out_torque=None,
+                  out_robot_wrench=None, robot_wrench: bool = False):
+        """Same, RigidPrimView layout: ``get_world_poses()`` -> (N,3), (N,4) and ``get_velocities()`` ->
+        (N,6) = [v, w] (hydrodynamics_behavior.py:178-189), consumed as they are (no slicing copies)."""
+        F, T, W = self._outputs(out_force, out_torque, out_robot_wrench, robot_wrench)
+        dl = _DL()
+        L.check(self._lib.h2o_step_view_dl(self._h, dl(position), dl(orientation_quat), dl(velocities), float(dt),
+                                           dl(F), dl(T), dl(W), _stream_ptr(self.device)))
+        return (F, T) if W is None else (F, T, W)
+
     def bind(self, position=None, orientation_quat=None, linear_vel=None, angular_vel=None, *,
              transforms=None, velocities=None, out_force=None, out_torque=None, out_robot_wrench=None,
              robot_wrench: bool = False):
@@ -251,6 +261,10 @@ class HydroEngine:
             L.check(self._lib.h2o_bind_dl(self._h, L.LAYOUT_PHYSX, dl(transforms), None, dl(velocities), None,
                                           dl(F), dl(T), dl(W)))
             self._bound = (transforms, velocities, F, T, W)
+        elif velocities is not None:
+            L.check(self._lib.h2o_bind_dl(self._h, L.LAYOUT_VIEW, dl(position), dl(orientation_quat), dl(velocities),
+                                          None, dl(F), dl(T), dl(W)))
+            self._bound = (position, orientation_quat, velocities, F, T, W)
         else:
             L.check(self._lib.h2o_bind_dl(self._h, L.LAYOUT_SPLIT, dl(position), dl(orientation_quat),
                                           dl(linear_vel), dl(angular_vel), dl(F), dl(T), dl(W)))

@@ -46,6 +46,9 @@ def _run_step(e, wl, dtype, dev, layout="split", robot=False):
     if layout == "split":
         out = e.step(_t(wl.pos, dtype, dev), _t(wl.quat_xyzw, dtype, dev), _t(wl.lin_vel, dtype, dev),
                      _t(wl.ang_vel, dtype, dev), wl.dt, robot_wrench=robot)
+    elif layout == "view":
+        out = e.step_view(_t(wl.pos, dtype, dev), _t(wl.quat_xyzw, dtype, dev), _t(wl.velocities(), dtype, dev),
+                          wl.dt, robot_wrench=robot)
     else:
         out = e.step_physx(_t(wl.transforms(), dtype, dev), _t(wl.velocities(), dtype, dev), wl.dt,
                            robot_wrench=robot)
@@ -67,7 +70,7 @@ def _check(wl, dtype, ref, F, T, what):
 # --------------------------------------------------------------------------- fused step
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["fp32", "fp64"])
 @pytest.mark.parametrize("kernel", ["tile", "direct"])
-@pytest.mark.parametrize("layout", ["split", "physx"])
+@pytest.mark.parametrize("layout", ["split", "physx", "view"])
 def test_step_heterogeneous_boxes(oracle, dev, dtype, kernel, layout):
     """C3 distribution, per-body records; n is deliberately not a multiple of the tile size."""
     wl = W.heterogeneous_boxes(100_003, seed=W.SEED_BASE + 33)
@@ -88,7 +91,7 @@ def test_step_hexapod_table_and_robot_wrench(oracle, dev, dtype, kernel):
     wl = W.hexapod_envs(2048 + 3)
     ref = _ref(oracle, wl)
     e = _engine(wl, dtype, dev, kernel)
-    F, T, Wr = _run_step(e, wl, dtype, dev, "split", robot=True)
+    F, T, Wr = _run_step(e, wl, dtype, dev, "view" if kernel == "tile" else "split", robot=True)
     _check(wl, dtype, ref, F, T, f"C2 {kernel}")
     want = oracle.robot_wrench(wl.pos, ref.force, ref.torque, wl.bodies_per_robot)
     err, den = scoring.vec_err(Wr, want)
