@@ -970,6 +970,9 @@ int h2o_step_host(h2o_handle h, const void* pos, const void* quat, const void* l
     for (int i = 0; i < 4; ++i)
         if (!in[i]) return fail(H2O_ERR_BAD_ARGUMENT, "NULL host input %d", i);
     if (!out_force || !out_torque) return fail(H2O_ERR_BAD_ARGUMENT, "NULL host output");
+    if (out_robot_wrench && e->bodies_per_robot <= 0)
+        return fail(H2O_ERR_NOT_CONFIGURED, "robot wrench requested but h2o_set_articulation not called");
+    if (e->param_mode < 0) return fail(H2O_ERR_NOT_CONFIGURED, "no parameters set (h2o_set_params_*)");
     if (!(dt > 1e-6)) return H2O_OK;
     DeviceGuard g(e->device);
     if (int rc = hp_init(e)) return rc;
