@@ -82,6 +82,16 @@ H2O_API int h2o_destroy(h2o_handle h);
 /* waterDensity, gravity (hydrodynamics_behavior.py:30-31; hydrodynamics_config.json "globals") */
 H2O_API int h2o_set_globals(h2o_handle h, double water_density, double gravity);
 
+/* Dense added mass.  calculate_added_mass (numba_hydrodynamics.py:219-253) takes
+ * ANY 6x6 body-frame matrix M: f6 = -M [R^T a; R^T alpha], F = R f6[0:3] ratio, tau = R f6[3:6] ratio;
+ * the wrapper only ever builds a diagonal one (numba_hydrodynamics_wrapper.py:101-112).  This call
+ * installs n_types row-major 6x6 matrices (host, float64) and a slot -> matrix map: body i uses
+ * matrices[slot_type[i % n_slots]] INSTEAD of the C_a / C_a_omega diagonal of its coefficient record.
+ * slot_type may be NULL when n_types == 1.  n_types == 0 restores the diagonal.  Steps with dense
+ * matrices run on the per-body kernel (H2O_KERNEL_DIRECT); h2o_components keeps the diagonal. */
+H2O_API int h2o_set_added_mass_dense(h2o_handle h, int n_types, const double* matrices, int n_slots,
+                                     const int32_t* slot_type);
+
 /* Generalisation the reference's signatures admit but its scenes never use:
  * a uniform water current (drag, damping and lift then see v - current) and the height of the flat
  * water surface (the reference's is the plane z = 0).  NULL / 0 = the reference's behaviour. */

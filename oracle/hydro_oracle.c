@@ -447,6 +447,42 @@ ORACLE_API void oracle_net_wrench(const oracle_out_t *c, const double position[3
     if (scale_out) *scale_out = scale;
 }
 
+/* Optional dense added-mass matrices for the batched drivers.  calculate_added_mass
+ * (numba_hydrodynamics.py:219-253) multiplies by whatever 6x6 it is handed; the wrapper only
+ * builds a diagonal one (numba_hydrodynamics_wrapper.py:101-112).  With n_types > 0, body i of a
+ * batch uses M[slot_type[i % n_slots]] instead of that diagonal.  n_types = 0 switches it off. */
+#define ORACLE_MAX_DENSE_TYPES 64
+#define ORACLE_MAX_DENSE_SLOTS 256
+static int g_dense_types = 0, g_dense_slots = 0;
+static double g_dense[ORACLE_MAX_DENSE_TYPES][6][6];
+static int32_t g_dense_slot[ORACLE_MAX_DENSE_SLOTS];
+
+ORACLE_API int oracle_set_added_mass_dense(int n_types, const double *M, int n_slots,
+                                           const int32_t *slot_type)
+{
+    if (n_types <= 0) {
+        g_dense_types = g_dense_slots = 0;
+        return 0;
+    }
+    if (n_types > ORACLE_MAX_DENSE_TYPES || n_slots < 1 || n_slots > ORACLE_MAX_DENSE_SLOTS || !M ||
+        !slot_type)
+        return 1;
+    for (int i = 0; i < n_slots; ++i)
+        if (slot_type[i] < 0 || slot_type[i] >= n_types) return 1;
+    memcpy(g_dense, M, (size_t)n_types * 36 * sizeof(double));
+    memcpy(g_dense_slot, slot_type, (size_t)n_slots * sizeof(int32_t));
+    g_dense_types = n_types;
+    g_dense_slots = n_slots;
+    return 0;
+}
+
+static inline void apply_dense_added_mass(oracle_body_t *b, int64_t i)
+{
+    if (g_dense_types > 0)
+        memcpy(b->added_mass_matrix, g_dense[g_dense_slot[i % g_dense_slots]],
+               sizeof b->added_mass_matrix);
+}
+
 /* ------------------------------------------------------------------------- */
 /* Batched drivers (one body per iteration, OpenMP over bodies).              */
 /* ------------------------------------------------------------------------- */
@@ -469,6 +505,7 @@ ORACLE_API void oracle_components_batch(int64_t n, const double *ctor, int64_t c
 #pragma omp for schedule(static)
         for (int64_t i = 0; i < n; ++i) {
             if (ctor_stride != 0) oracle_body_init(&body, ctor + i * ctor_stride);
+            apply_dense_added_mass(&body, i);
             oracle_solve(&body, pos + 3 * i, quat_xyzw + 4 * i, lin_vel + 3 * i, ang_vel + 3 * i,
                          lin_acc + 3 * i, ang_acc + 3 * i, &out[i]);
         }
@@ -498,6 +535,7 @@ ORACLE_API void oracle_step_batch(int64_t n, const double *ctor, int64_t ctor_st
 #pragma omp for schedule(static)
         for (int64_t i = 0; i < n; ++i) {
             if (ctor_stride != 0) oracle_body_init(&body, ctor + i * ctor_stride);
+            apply_dense_added_mass(&body, i);
             double q[4], a[3], al[3];
             if (quat_wxyz) {
                 q[0] = quat[4 * i + 1];

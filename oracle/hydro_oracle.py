@@ -79,6 +79,19 @@ def set_warp_compat(enable: bool) -> None:
     lib().oracle_set_warp_compat(ctypes.c_int(1 if enable else 0))
 
 
+def set_added_mass_dense(matrices=None, slot_type=None) -> None:
+    """Dense 6x6 added-mass matrices for the batched drivers: body i uses
+    ``matrices[slot_type[i % len(slot_type)]]``; ``None`` restores the wrapper's diagonal."""
+    if matrices is None:
+        lib().oracle_set_added_mass_dense(0, None, 0, None)
+        return
+    m = np.ascontiguousarray(np.asarray(matrices, dtype=np.float64)).reshape(-1, 6, 6)
+    st = np.ascontiguousarray(np.zeros(1) if slot_type is None else slot_type, dtype=np.int32)
+    rc = lib().oracle_set_added_mass_dense(ctypes.c_int(m.shape[0]), _ptr(m), ctypes.c_int(st.size), _ptr(st))
+    if rc != 0:
+        raise ValueError("bad dense added-mass table")
+
+
 def max_threads() -> int:
     return int(lib().oracle_max_threads())
 

@@ -38,8 +38,13 @@ def load():
     return NumbaHydrodynamicsWrapper, solve_hydrodynamics
 
 
-def components_via_wrapper(ctor_rows, pos, quat_xyzw, lin_vel, ang_vel, lin_acc, ang_acc):
+def components_via_wrapper(ctor_rows, pos, quat_xyzw, lin_vel, ang_vel, lin_acc, ang_acc,
+                           dense=None, dense_slot=None):
     """Call the reference wrapper once per body (how it is meant to be used).
+
+    ``dense`` (n_types,6,6) + ``dense_slot``: body i's wrapper instance gets
+    ``_added_mass_matrix = dense[dense_slot[i % len(dense_slot)]]`` after construction, i.e. the
+    unmodified ``solve_hydrodynamics`` / ``calculate_added_mass`` run with a full matrix.
 
     Returns (records, raised) where ``records`` uses hydro_oracle.OUT_DTYPE and
     ``raised[i]`` is True when the reference threw TypeError.
@@ -56,9 +61,12 @@ def components_via_wrapper(ctor_rows, pos, quat_xyzw, lin_vel, ang_vel, lin_acc,
     cache = {}
     for i in range(n):
         row = tuple(ctor_rows[i] if ctor_rows.ndim == 2 else ctor_rows)
-        w = cache.get(row)
+        ty = -1 if dense is None else int(dense_slot[i % len(dense_slot)])
+        w = cache.get((row, ty))
         if w is None:
-            w = cache[row] = Wrapper(*row)
+            w = cache[(row, ty)] = Wrapper(*row)
+            if ty >= 0:
+                w._added_mass_matrix = np.ascontiguousarray(dense[ty], dtype=np.float64)
         try:
             r = w.calculate_hydrodynamic_forces(pos[i], quat_xyzw[i], lin_vel[i], ang_vel[i],
                                                 lin_acc[i], ang_acc[i])

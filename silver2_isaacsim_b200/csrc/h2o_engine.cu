@@ -71,6 +71,9 @@ struct h2o_engine {
     int64_t launches = 0;
     int sm_count = 148;
     int tile_cfg = 0;          // 0 = default configuration of the dtype
+    void* am_dense = nullptr;  // (am_types, 6, 6) dense added-mass matrices in the engine dtype, or nullptr
+    int32_t* am_slot_type = nullptr;
+    int am_types = 0, am_slots = 0;
     int max_ctas_per_sm = 0;   // 0 = as many as fit
     int warp_compat = 0;       // components entry point reproduces the Warp twin's deviations
     int robot_cfg = -1;        // -1 = pick the CTA size by lane utilisation (tuning override: 0,1,2)
@@ -278,6 +281,7 @@ static int step_typed2(h2o_engine* e, StepArgs& a, cudaStream_t stream)
     if (e->kernel_choice == H2O_KERNEL_TILE) use_tile = true;
     else if (e->kernel_choice == H2O_KERNEL_AUTO) use_tile = a.n >= (long long)e->sm_count * 256;
     if (TB == 0 || !ptr_ok || a.n < TB) use_tile = false;
+    if (a.am_dense) use_tile = false;  // dense added mass: direct kernel (+ robot_wrench_kernel)
 
     long long done_bodies = 0;
     if (use_tile) {
@@ -387,6 +391,7 @@ static int step_device(h2o_engine* e, int layout, const void* pos, const void* q
     a.rho = e->rho; a.grav = e->grav; a.inv_dt = 1.0 / dt;
     for (int k = 0; k < 3; ++k) a.current[k] = e->current[k];
     a.surface_z = e->surface_z;
+    a.am_dense = e->am_dense; a.am_slot_type = e->am_slot_type; a.am_n_slots = e->am_slots;
     return e->dtype == H2O_F32 ? step_typed<float>(e, layout, a, stream) : step_typed<double>(e, layout, a, stream);
 }
 
@@ -474,6 +479,8 @@ int h2o_destroy(h2o_handle h)
     if (e->capture_stream) cudaStreamDestroy(e->capture_stream);
     if (e->coeff) cudaFree(e->coeff);
     if (e->slot_type) cudaFree(e->slot_type);
+    if (e->am_dense) cudaFree(e->am_dense);
+    if (e->am_slot_type) cudaFree(e->am_slot_type);
     if (e->prev) cudaFree(e->prev);
     if (e->stats) cudaFree(e->stats);
     e->magic = 0;
@@ -530,6 +537,51 @@ int h2o_set_part_table(h2o_handle h, int n_types, const double* table_host, int 
     e->n_types = n_types;
     e->n_slots = n_slots;
     e->coeff_rows = n_types;
+    return H2O_OK;
+}
+
+int h2o_set_added_mass_dense(h2o_handle h, int n_types, const double* matrices_host, int n_slots,
+                             const int32_t* slot_type_host)
+{
+    h2o_engine* e = check(h);
+    if (!e) return H2O_ERR_BAD_HANDLE;
+    DeviceGuard g(e->device);
+    if (n_types == 0) {  // back to the wrapper's diagonal
+        if (e->am_dense) { cudaFree(e->am_dense); e->am_dense = nullptr; }
+        if (e->am_slot_type) { cudaFree(e->am_slot_type); e->am_slot_type = nullptr; }
+        e->am_types = e->am_slots = 0;
+        return H2O_OK;
+    }
+    if (n_types < 0 || n_types > MAX_TABLE_TYPES)
+        return fail(H2O_ERR_BAD_ARGUMENT, "n_types %d out of range [0,%d]", n_types, MAX_TABLE_TYPES);
+    if (!matrices_host) return fail(H2O_ERR_BAD_ARGUMENT, "matrices is NULL");
+    const int32_t slot0 = 0;
+    if (!slot_type_host) {
+        if (n_types != 1) return fail(H2O_ERR_BAD_ARGUMENT, "slot_type is NULL with %d matrices", n_types);
+        slot_type_host = &slot0;
+        n_slots = 1;
+    }
+    if (n_slots < 1 || n_slots > MAX_TABLE_SLOTS)
+        return fail(H2O_ERR_BAD_ARGUMENT, "n_slots %d out of range [1,%d]", n_slots, MAX_TABLE_SLOTS);
+    for (int i = 0; i < n_slots; ++i)
+        if (slot_type_host[i] < 0 || slot_type_host[i] >= n_types)
+            return fail(H2O_ERR_BAD_ARGUMENT, "slot_type[%d] = %d out of range", i, slot_type_host[i]);
+    if (e->am_dense) { cudaFree(e->am_dense); e->am_dense = nullptr; }
+    if (e->am_slot_type) { cudaFree(e->am_slot_type); e->am_slot_type = nullptr; }
+    e->am_types = e->am_slots = 0;
+    const size_t cnt = size_t(n_types) * 36;
+    CUDA_TRY(cudaMalloc(&e->am_dense, cnt * e->esz));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&e->am_slot_type), n_slots * sizeof(int32_t)));
+    if (e->dtype == H2O_F32) {
+        std::vector<float> tmp(cnt);
+        for (size_t i = 0; i < cnt; ++i) tmp[i] = float(matrices_host[i]);
+        CUDA_TRY(cudaMemcpy(e->am_dense, tmp.data(), cnt * sizeof(float), cudaMemcpyHostToDevice));
+    } else {
+        CUDA_TRY(cudaMemcpy(e->am_dense, matrices_host, cnt * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    CUDA_TRY(cudaMemcpy(e->am_slot_type, slot_type_host, n_slots * sizeof(int32_t), cudaMemcpyHostToDevice));
+    e->am_types = n_types;
+    e->am_slots = n_slots;
     return H2O_OK;
 }
 

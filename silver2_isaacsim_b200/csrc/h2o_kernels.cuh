@@ -65,6 +65,12 @@ struct StepArgs {
     double rho, grav, inv_dt;
     double current[3];       // uniform water current (world): the flow-relative velocity is v - current
     double surface_z;        // height of the (flat) water surface; the reference's is z = 0
+    // optional dense added mass: (am_n_types, 6, 6) row-major in the engine dtype and
+    // its own slot -> matrix map; body i uses am_slot_type[(first_body + i) % am_n_slots].  Served by
+    // the direct kernel only (the tile kernel keeps the wrapper's diagonal).
+    const void* am_dense;
+    const int32_t* am_slot_type;
+    int am_n_slots;
 };
 
 // ---------------------------------------------------------------------------
@@ -234,6 +240,7 @@ __device__ __forceinline__ void make_body_in(const RawBody<S>& r, const S* c, in
     in.c_am = c[7]; in.c_am_ang = c[8]; in.c_lift = c[9];
     in.rho_h = rho; in.grav_h = grav; in.rho = S(rho);
     in.warp_compat = false;
+    in.am_dense = nullptr;
 }
 
 // Running statistics kept in registers across a thread's bodies.
@@ -584,6 +591,8 @@ __global__ void __launch_bounds__(256) step_direct_kernel(const __grid_constant_
         }
         BodyIn<double, S> bin;
         make_body_in<S>(r, cl, a.quat_wxyz, a.rho, a.grav, S(a.inv_dt), Env{a.current[0], a.current[1], a.current[2], a.surface_z}, bin);
+        if (a.am_dense)
+            bin.am_dense = reinterpret_cast<const S*>(a.am_dense) + 36 * a.am_slot_type[(a.first_body + i) % a.am_n_slots];
         S F[3], T[3];
         body_step<S>(bin, cl[10], F, T, kStats ? &st : nullptr);
         S* of = reinterpret_cast<S*>(a.out_force) + 3 * i;

@@ -180,6 +180,9 @@ template <typename H, typename L> struct BodyIn {
                           // reference's Warp twin does (warp_hydrodynamics.py:216-217)
     H rho_h, grav_h;      // globals: waterDensity, gravity (H for buoyancy)
     L rho;                // = L(rho_h)
+    const L* am_dense;    // optional dense 6x6 added-mass matrix, row-major, body frame (the matrix
+                          // calculate_added_mass takes, numba_hydrodynamics.py:220); nullptr = the
+                          // wrapper's diagonal built from c_am / c_am_ang (wrapper :101-112)
 };
 
 template <typename H, typename L> struct Terms {
@@ -389,22 +392,34 @@ H2O_HD void body_terms(const BodyIn<H, L>& in, Terms<H, L>& t)
     // ---- added mass (numba_hydrodynamics.py:224-253; diagonal of
     //      numba_hydrodynamics_wrapper.py:101-112): -R diag(M) R^T acc * ratio
     {
-        const L ml = vol * in.c_am * in.rho * rl;
         const bool fwd = in.warp_compat;  // Numba: R^T a (numba_hydrodynamics.py:229-230); Warp twin: R a
         const L lx = fwd ? r00 * in.ax + r01 * in.ay + r02 * in.az : r00 * in.ax + r10 * in.ay + r20 * in.az;
         const L ly = fwd ? r10 * in.ax + r11 * in.ay + r12 * in.az : r01 * in.ax + r11 * in.ay + r21 * in.az;
         const L lz = fwd ? r20 * in.ax + r21 * in.ay + r22 * in.az : r02 * in.ax + r12 * in.ay + r22 * in.az;
-        const L fx = -(ml * lx), fy = -(ml * ly), fz = -(ml * lz);
-        t.fam[0] = r00 * fx + r01 * fy + r02 * fz;
-        t.fam[1] = r10 * fx + r11 * fy + r12 * fz;
-        t.fam[2] = r20 * fx + r21 * fy + r22 * fz;
-
-        const L ma = vol * in.c_am_ang * in.rho * rl;
-        const L w2s = in.dimx * in.dimx, d2s = in.dimy * in.dimy, h2s = in.dimz * in.dimz;
         const L gx = fwd ? r00 * in.bx + r01 * in.by + r02 * in.bz : r00 * in.bx + r10 * in.by + r20 * in.bz;
         const L gy = fwd ? r10 * in.bx + r11 * in.by + r12 * in.bz : r01 * in.bx + r11 * in.by + r21 * in.bz;
         const L gz = fwd ? r20 * in.bx + r21 * in.by + r22 * in.bz : r02 * in.bx + r12 * in.by + r22 * in.bz;
-        const L tx = -(ma * (d2s + h2s) * gx), ty = -(ma * (w2s + h2s) * gy), tz = -(ma * (w2s + d2s) * gz);
+        L fx, fy, fz, tx, ty, tz;
+        if (in.am_dense) {  // f6 = -M [a_b; alpha_b]  (numba_hydrodynamics.py:232-243), any 6x6
+            const L a6[6] = {lx, ly, lz, gx, gy, gz};
+            L f6[6];
+            for (int i = 0; i < 6; ++i) {
+                L acc = L(0);
+                for (int j = 0; j < 6; ++j) acc += in.am_dense[6 * i + j] * a6[j];
+                f6[i] = -(acc * rl);
+            }
+            fx = f6[0]; fy = f6[1]; fz = f6[2];
+            tx = f6[3]; ty = f6[4]; tz = f6[5];
+        } else {
+            const L ml = vol * in.c_am * in.rho * rl;
+            fx = -(ml * lx); fy = -(ml * ly); fz = -(ml * lz);
+            const L ma = vol * in.c_am_ang * in.rho * rl;
+            const L w2s = in.dimx * in.dimx, d2s = in.dimy * in.dimy, h2s = in.dimz * in.dimz;
+            tx = -(ma * (d2s + h2s) * gx); ty = -(ma * (w2s + h2s) * gy); tz = -(ma * (w2s + d2s) * gz);
+        }
+        t.fam[0] = r00 * fx + r01 * fy + r02 * fz;
+        t.fam[1] = r10 * fx + r11 * fy + r12 * fz;
+        t.fam[2] = r20 * fx + r21 * fy + r22 * fz;
         t.tam[0] = r00 * tx + r01 * ty + r02 * tz;
         t.tam[1] = r10 * tx + r11 * ty + r12 * tz;
         t.tam[2] = r20 * tx + r21 * ty + r22 * tz;
@@ -601,19 +616,38 @@ H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], boo
     const L tl = d2 * sl;
     const L flx = -(d0 * tl), fly = -(d1 * tl), flz = an2 * sl;  // body frame
 
-    // ---- added mass: force in the world frame, inertia torque in the body frame
+    // ---- added mass: isotropic force in the world frame (R m I R^T = m I), inertia torque in the
+    //      body frame; a dense matrix (am_dense) keeps both in the body frame
     const L rv = vol * in.rho * rl * in.acc_scale;
-    const L ml = rv * in.c_am;
-    const L ma = rv * in.c_am_ang;
-    const L w2s = in.dimx * in.dimx, d2s = in.dimy * in.dimy, h2s = in.dimz * in.dimz;
     const L bbx = r00 * in.bx + r10 * in.by + r20 * in.bz;
     const L bby = r01 * in.bx + r11 * in.by + r21 * in.bz;
     const L bbz = r02 * in.bx + r12 * in.by + r22 * in.bz;
-
-    // ---- body-frame torque: psi*(...) + arm x F_l + added inertia (buoyancy torque: tbuoy, above)
-    const L tbx = psi * tdx + ((army * flz - armz * fly) - ma * (d2s + h2s) * bbx);
-    const L tby = psi * tdy + ((armz * flx - armx * flz) - ma * (w2s + h2s) * bby);
-    const L tbz = psi * tdz + ((armx * fly - army * flx) - ma * (w2s + d2s) * bbz);
+    L ml, ffx, ffy, ffz, tbx, tby, tbz;
+    if (in.am_dense) {
+        const L a6[6] = {r00 * in.ax + r10 * in.ay + r20 * in.az, r01 * in.ax + r11 * in.ay + r21 * in.az,
+                         r02 * in.ax + r12 * in.ay + r22 * in.az, bbx, bby, bbz};
+        const L sc = rl * in.acc_scale;
+        L f6[6];
+        for (int i = 0; i < 6; ++i) {
+            L acc = L(0);
+            for (int j = 0; j < 6; ++j) acc += in.am_dense[6 * i + j] * a6[j];
+            f6[i] = acc * sc;
+        }
+        ml = L(0);
+        ffx = flx - f6[0]; ffy = fly - f6[1]; ffz = flz - f6[2];
+        tbx = psi * tdx + ((army * flz - armz * fly) - f6[3]);
+        tby = psi * tdy + ((armz * flx - armx * flz) - f6[4]);
+        tbz = psi * tdz + ((armx * fly - army * flx) - f6[5]);
+    } else {
+        ml = rv * in.c_am;
+        const L ma = rv * in.c_am_ang;
+        const L w2s = in.dimx * in.dimx, d2s = in.dimy * in.dimy, h2s = in.dimz * in.dimz;
+        ffx = flx; ffy = fly; ffz = flz;
+        // ---- body-frame torque: psi*(...) + arm x F_l + added inertia (buoyancy torque: tbuoy, above)
+        tbx = psi * tdx + ((army * flz - armz * fly) - ma * (d2s + h2s) * bbx);
+        tby = psi * tdy + ((armz * flx - armx * flz) - ma * (w2s + h2s) * bby);
+        tbz = psi * tdz + ((armx * fly - army * flx) - ma * (w2s + d2s) * bbz);
+    }
 
     // ---- angular drag (world): -(0.5 rho |w| C V + k min(1, 5|w|)) ratio * w
     const L as2 = in.wx * in.wx + in.wy * in.wy + in.wz * in.wz;
@@ -625,9 +659,9 @@ H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], boo
     T[1] = ((r10 * tbx + r11 * tby + r12 * tbz) - ka * in.wy) + tbuoy_y;
     T[2] = (r20 * tbx + r21 * tby + r22 * tbz) - ka * in.wz;
 
-    F[0] = (r00 * flx + r01 * fly + r02 * flz) - (gam * in.vx + ml * in.ax);
-    F[1] = (r10 * flx + r11 * fly + r12 * flz) - (gam * in.vy + ml * in.ay);
-    const L fz = (r20 * flx + r21 * fly + r22 * flz) - (gam * in.vz + ml * in.az);
+    F[0] = (r00 * ffx + r01 * ffy + r02 * ffz) - (gam * in.vx + ml * in.ax);
+    F[1] = (r10 * ffx + r11 * ffy + r12 * ffz) - (gam * in.vy + ml * in.ay);
+    const L fz = (r20 * ffx + r21 * ffy + r22 * ffz) - (gam * in.vz + ml * in.az);
     F[2] = L(fbz + H(fz));
 
     // ---- safety clamp (hydrodynamics_behavior.py:221-226)

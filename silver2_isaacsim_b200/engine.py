@@ -110,6 +110,29 @@ class HydroEngine:
         arr = (ctypes.c_double * 3)(*[float(x) for x in current])
         L.check(self._lib.h2o_set_environment(self._h, arr, float(surface_z)))
 
+    def set_added_mass_dense(self, matrices=None, slot_type=None):
+        """Dense 6x6 body-frame added-mass matrices (the argument ``calculate_added_mass`` takes,
+        numba_hydrodynamics.py:220) instead of the wrapper's diagonal: ``matrices`` is (6,6) or
+        (n_types,6,6), body ``i`` uses ``matrices[slot_type[i % len(slot_type)]]``.  ``None`` restores
+        the diagonal.  Steps then run on the per-body kernel."""
+        if matrices is None:
+            L.check(self._lib.h2o_set_added_mass_dense(self._h, 0, None, 0, None))
+            return
+        m = np.ascontiguousarray(np.asarray(matrices, dtype=np.float64))
+        if m.ndim == 2:
+            m = m[None]
+        if m.ndim != 3 or m.shape[1:] != (6, 6):
+            raise ValueError("matrices must be (6,6) or (n_types,6,6)")
+        mp = m.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        if slot_type is None:
+            if m.shape[0] != 1:
+                raise ValueError("slot_type is required with more than one matrix")
+            L.check(self._lib.h2o_set_added_mass_dense(self._h, 1, mp, 1, None))
+            return
+        st = np.ascontiguousarray(np.asarray(slot_type, dtype=np.int32))
+        L.check(self._lib.h2o_set_added_mass_dense(self._h, int(m.shape[0]), mp, int(st.size),
+                                                   st.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+
     def set_params_uniform(self, ctor12: Sequence[float], mass: float):
         """Same twelve scalars, same order, as the reference wrapper ctor
         (numba_hydrodynamics_wrapper.py:9-10) + the body mass used by the clamp."""

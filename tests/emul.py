@@ -39,3 +39,20 @@ def step(wl, mode, exact_trig=0):
                          ctypes.c_double(wl.g), ctypes.c_double(wl.dt), p(F), p(T), p(comp), p(masks))
     assert rc == 0
     return F, T, comp, masks
+
+
+def step_dense(wl, mode, matrices, slot_type):
+    """Fused step with dense added-mass matrices (n_types,6,6); body i uses matrices[slot_type[i % n_slots]]."""
+    n = wl.n
+    d = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    F, T = np.zeros((n, 3)), np.zeros((n, 3))
+    m = d(matrices).reshape(-1, 6, 6)
+    st = np.ascontiguousarray(slot_type, dtype=np.int32)
+    arrs = [d(wl.pos), d(wl.quat_xyzw), d(wl.lin_vel), d(wl.ang_vel), d(wl.prev_lin), d(wl.prev_ang),
+            d(wl.coeff_per_body())]
+    rc = lib().emul_step_dense(mode, ctypes.c_int64(n), *[p(a) for a in arrs], ctypes.c_double(wl.rho),
+                               ctypes.c_double(wl.g), ctypes.c_double(wl.dt), p(F), p(T), p(m), p(st),
+                               ctypes.c_int(st.size))
+    assert rc == 0
+    return F, T

@@ -14,7 +14,8 @@ using namespace h2o;
 template <typename S, typename H, typename L, bool kExactTrig, bool kFast = false>
 static void run(int64_t n, const double* pos, const double* quat, const double* v, const double* w,
                 const double* pl, const double* pa, const double* coeff, double rho, double g,
-                double dt, double* F, double* T, double* comp, uint32_t* masks)
+                double dt, double* F, double* T, double* comp, uint32_t* masks, const double* dense = nullptr,
+                const int32_t* dense_slot = nullptr, int dense_slots = 0)
 {
     const L inv_dt = L(1.0 / dt);
     for (int64_t i = 0; i < n; ++i) {
@@ -41,6 +42,13 @@ static void run(int64_t n, const double* pos, const double* quat, const double* 
         in.c_am = L(S(c[7])); in.c_am_ang = L(S(c[8])); in.c_lift = L(S(c[9]));
         in.rho_h = H(rho); in.grav_h = H(g); in.rho = L(rho);
         in.warp_compat = false;
+        L mloc[36];
+        in.am_dense = nullptr;
+        if (dense) {
+            const double* m = dense + 36 * dense_slot[i % dense_slots];
+            for (int k = 0; k < 36; ++k) mloc[k] = L(S(m[k]));
+            in.am_dense = mloc;
+        }
         Terms<H, L> t;
         L f[3], tq[3];
         bool clamped;
@@ -89,6 +97,26 @@ int emul_step(int mode, int exact_trig, int64_t n, const double* pos, const doub
         case 3: GO(float, double, double); return 0;    // fp32 storage, all-fp64 arithmetic
         case 4: run<float, double, float, false, true>(n, pos, quat, v, w, pl, pa, coeff, rho, g, dt, F, T, comp, masks);
                 return 0;                               // fp32 mode, fused-step fast path (body frame)
+    }
+    return 1;
+}
+
+// Same, with dense added-mass matrices (n_types,6,6) + slot map; modes 0 and 4 only.
+extern "C" __attribute__((visibility("default")))
+int emul_step_dense(int mode, int64_t n, const double* pos, const double* quat, const double* v,
+                    const double* w, const double* pl, const double* pa, const double* coeff, double rho,
+                    double g, double dt, double* F, double* T, const double* dense, const int32_t* dense_slot,
+                    int dense_slots)
+{
+    if (mode == 0) {
+        run<double, double, double, false>(n, pos, quat, v, w, pl, pa, coeff, rho, g, dt, F, T, nullptr, nullptr,
+                                           dense, dense_slot, dense_slots);
+        return 0;
+    }
+    if (mode == 4) {
+        run<float, double, float, false, true>(n, pos, quat, v, w, pl, pa, coeff, rho, g, dt, F, T, nullptr, nullptr,
+                                               dense, dense_slot, dense_slots);
+        return 0;
     }
     return 1;
 }
