@@ -8,7 +8,7 @@ n = int(os.environ.get("N", 1 << 20)); steps = int(os.environ.get("STEPS", 8))
 dtype = torch.float64 if os.environ.get("DTYPE", "f32") == "f64" else torch.float32
 kind = os.environ.get("WL", "c3")
 dev = torch.device("cuda:0")
-wl = W.heterogeneous_boxes(n) if kind == "c3" else W.hexapod_envs(n // 19)
+wl = W.heterogeneous_boxes(n) if kind == "c3" else (W.sharded_robots(n // 19) if kind == "c4" else W.hexapod_envs(n // 19))
 eng = HydroEngine(wl.n, dtype=dtype, device=dev); eng.set_workload_params(wl)
 eng.set_kernel(os.environ.get("KERNEL", "tile"))
 npdt = np.float32 if dtype == torch.float32 else np.float64
