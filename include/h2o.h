@@ -82,6 +82,14 @@ H2O_API int h2o_destroy(h2o_handle h);
 /* waterDensity, gravity (hydrodynamics_behavior.py:30-31; hydrodynamics_config.json "globals") */
 H2O_API int h2o_set_globals(h2o_handle h, double water_density, double gravity);
 
+/* Non-flat water surface: eta is a DEVICE array (n_bodies,) in the handle's dtype
+ * holding the surface elevation above surface_z at each body's position (e.g. a wave field sampled
+ * by the caller); the model then sees p_z - surface_z - eta[i] where the reference uses p_z
+ * (analyze_submersion_and_cob, numba_hydrodynamics.py:59-105, tests keypoints against z = 0).  The
+ * pointer is borrowed and read by every later step until replaced; NULL = flat.  Steps with a
+ * height field run on the per-body kernel. */
+H2O_API int h2o_set_surface_heights(h2o_handle h, const void* eta_dev);
+
 /* Dense added mass.  calculate_added_mass (numba_hydrodynamics.py:219-253) takes
  * ANY 6x6 body-frame matrix M: f6 = -M [R^T a; R^T alpha], F = R f6[0:3] ratio, tau = R f6[3:6] ratio;
  * the wrapper only ever builds a diagonal one (numba_hydrodynamics_wrapper.py:101-112).  This call

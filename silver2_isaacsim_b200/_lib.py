@@ -48,6 +48,7 @@ SIGNATURES = {
     "h2o_destroy": (c_int, [_P]),
     "h2o_set_globals": (c_int, [_P, c_double, c_double]),
     "h2o_set_environment": (c_int, [_P, POINTER(c_double), c_double]),
+    "h2o_set_surface_heights": (c_int, [_P, _P]),
     "h2o_set_added_mass_dense": (c_int, [_P, c_int, POINTER(c_double), c_int, POINTER(c_int32)]),
     "h2o_set_params_uniform": (c_int, [_P, POINTER(c_double), c_double]),
     "h2o_set_part_table": (c_int, [_P, c_int, POINTER(c_double), c_int, POINTER(c_int32)]),

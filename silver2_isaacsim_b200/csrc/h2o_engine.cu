@@ -74,6 +74,7 @@ struct h2o_engine {
     void* am_dense = nullptr;  // (am_types, 6, 6) dense added-mass matrices in the engine dtype, or nullptr
     int32_t* am_slot_type = nullptr;
     int am_types = 0, am_slots = 0;
+    const void* surface_eta = nullptr;  // (n,) per-body surface heights, borrowed, or nullptr = flat
     int max_ctas_per_sm = 0;   // 0 = as many as fit
     int warp_compat = 0;       // components entry point reproduces the Warp twin's deviations
     int robot_cfg = -1;        // -1 = pick the CTA size by lane utilisation (tuning override: 0,1,2)
@@ -281,7 +282,7 @@ static int step_typed2(h2o_engine* e, StepArgs& a, cudaStream_t stream)
     if (e->kernel_choice == H2O_KERNEL_TILE) use_tile = true;
     else if (e->kernel_choice == H2O_KERNEL_AUTO) use_tile = a.n >= (long long)e->sm_count * 256;
     if (TB == 0 || !ptr_ok || a.n < TB) use_tile = false;
-    if (a.am_dense) use_tile = false;  // dense added mass: direct kernel (+ robot_wrench_kernel)
+    if (a.am_dense || a.surface_eta) use_tile = false;  // f4 generalisations: direct kernel (+ robot_wrench_kernel)
 
     long long done_bodies = 0;
     if (use_tile) {
@@ -392,6 +393,7 @@ static int step_device(h2o_engine* e, int layout, const void* pos, const void* q
     for (int k = 0; k < 3; ++k) a.current[k] = e->current[k];
     a.surface_z = e->surface_z;
     a.am_dense = e->am_dense; a.am_slot_type = e->am_slot_type; a.am_n_slots = e->am_slots;
+    a.surface_eta = e->surface_eta ? static_cast<const char*>(e->surface_eta) + size_t(first_body) * e->esz : nullptr;
     return e->dtype == H2O_F32 ? step_typed<float>(e, layout, a, stream) : step_typed<double>(e, layout, a, stream);
 }
 
@@ -503,6 +505,14 @@ int h2o_set_environment(h2o_handle h, const double current_xyz[3], double surfac
     if (!e) return H2O_ERR_BAD_HANDLE;
     for (int k = 0; k < 3; ++k) e->current[k] = current_xyz ? current_xyz[k] : 0.0;
     e->surface_z = surface_z;
+    return H2O_OK;
+}
+
+int h2o_set_surface_heights(h2o_handle h, const void* eta_dev)
+{
+    h2o_engine* e = check(h);
+    if (!e) return H2O_ERR_BAD_HANDLE;
+    e->surface_eta = eta_dev;
     return H2O_OK;
 }
 

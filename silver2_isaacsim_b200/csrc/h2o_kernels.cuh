@@ -71,6 +71,9 @@ struct StepArgs {
     const void* am_dense;
     const int32_t* am_slot_type;
     int am_n_slots;
+    // optional non-flat water surface: (N,) surface height above surface_z at each body's
+    // position, engine dtype, borrowed from the caller.  Direct kernel only.
+    const void* surface_eta;
 };
 
 // ---------------------------------------------------------------------------
@@ -590,7 +593,9 @@ __global__ void __launch_bounds__(256) step_direct_kernel(const __grid_constant_
             for (int k = 0; k < N_COEFF; ++k) cl[k] = c[k];
         }
         BodyIn<double, S> bin;
-        make_body_in<S>(r, cl, a.quat_wxyz, a.rho, a.grav, S(a.inv_dt), Env{a.current[0], a.current[1], a.current[2], a.surface_z}, bin);
+        Env env{a.current[0], a.current[1], a.current[2], a.surface_z};
+        if (a.surface_eta) env.surface_z += double(reinterpret_cast<const S*>(a.surface_eta)[i]);
+        make_body_in<S>(r, cl, a.quat_wxyz, a.rho, a.grav, S(a.inv_dt), env, bin);
         if (a.am_dense)
             bin.am_dense = reinterpret_cast<const S*>(a.am_dense) + 36 * a.am_slot_type[(a.first_body + i) % a.am_n_slots];
         S F[3], T[3];

@@ -110,6 +110,20 @@ class HydroEngine:
         arr = (ctypes.c_double * 3)(*[float(x) for x in current])
         L.check(self._lib.h2o_set_environment(self._h, arr, float(surface_z)))
 
+    def set_surface_heights(self, eta: Optional[torch.Tensor]):
+        """Non-flat water surface: ``eta`` (n,) on the engine's device / dtype holds the surface elevation
+        above ``surface_z`` at each body's position; it is read (not copied) by every later step, so the
+        caller may update it in place between steps.  ``None`` = flat.  Steps then run on the per-body
+        kernel."""
+        if eta is None:
+            L.check(self._lib.h2o_set_surface_heights(self._h, None))
+            self._eta = None
+            return
+        if eta.device != self.device or eta.dtype != self.dtype or tuple(eta.shape) != (self.n_bodies,) or not eta.is_contiguous():
+            raise ValueError(f"eta must be a contiguous ({self.n_bodies},) {self.dtype} tensor on {self.device}")
+        L.check(self._lib.h2o_set_surface_heights(self._h, ctypes.c_void_p(eta.data_ptr())))
+        self._eta = eta  # keep the borrowed memory alive
+
     def set_added_mass_dense(self, matrices=None, slot_type=None):
         """Dense 6x6 body-frame added-mass matrices (the argument ``calculate_added_mass`` takes,
         numba_hydrodynamics.py:220) instead of the wrapper's diagonal: ``matrices`` is (6,6) or

@@ -474,6 +474,34 @@ def test_environment_current_and_surface_height(oracle, dev, dtype):
     _check(wl, dtype, _ref(oracle, wl), F0, T0, "environment reset")
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["fp32", "fp64"])
+def test_surface_height_field(oracle, dev, dtype):
+    """f4: a non-flat surface (elevation sampled at every body) equals the reference model evaluated at
+    the surface-relative height p_z - eta_i; the array is borrowed, so in-place updates are seen."""
+    wl = W.heterogeneous_boxes(200_000, seed=77)     # past the tile threshold: must route to the per-body kernel
+    x, y = wl.pos[:, 0].astype(np.float64), wl.pos[:, 1].astype(np.float64)
+    eta = (0.3 * np.cos(0.7 * x + 0.2) + 0.15 * np.sin(1.3 * y - 0.4)).astype(np.float32)
+    e = _engine(wl, dtype, dev, "auto")
+    eta_t = torch.as_tensor(eta, device=dev).to(dtype)
+    e.set_surface_heights(eta_t)
+    F, T = _run_step(e, wl, dtype, dev)
+    assert e.last_kernel == "direct"
+    pos = wl.pos.astype(np.float64).copy()
+    pos[:, 2] -= eta.astype(np.float64)
+    ref = oracle.step(wl.ctor_rows(), wl.masses(), pos, wl.quat_xyzw, wl.lin_vel, wl.ang_vel,
+                      wl.prev_lin, wl.prev_ang, wl.dt)
+    _check(W.Workload(**{**wl.__dict__, "pos": pos}), dtype, ref, F, T, "surface height field")
+    eta_t.zero_()                                     # borrowed: the next step sees the flat surface again
+    F0, T0 = _run_step(e, wl, dtype, dev)
+    _check(wl, dtype, _ref(oracle, wl), F0, T0, "surface height field zeroed")
+    with pytest.raises(ValueError):
+        e.set_surface_heights(eta_t[:-1])
+    e.set_surface_heights(None)
+    e.set_kernel("tile")
+    _run_step(e, wl, dtype, dev)
+    assert e.last_kernel == "tile"
+
+
 def test_integration_md_raw_ctypes_snippet(dev):
     """The raw C-ABI binding shown in INTEGRATION.md section 3 (no helper layer) works as written."""
     import ctypes
