@@ -86,8 +86,9 @@ H2O_API int h2o_set_globals(h2o_handle h, double water_density, double gravity);
  * holding the surface elevation above surface_z at each body's position (e.g. a wave field sampled
  * by the caller); the model then sees p_z - surface_z - eta[i] where the reference uses p_z
  * (analyze_submersion_and_cob, numba_hydrodynamics.py:59-105, tests keypoints against z = 0).  The
- * pointer is borrowed and read by every later step until replaced; NULL = flat.  Steps with a
- * height field run on the per-body kernel. */
+ * pointer is borrowed and read by every later step until replaced (update the array in place between
+ * steps; a rollout captured with h2o_capture_rollout keeps the pointer it was captured with); NULL =
+ * flat.  Steps with a height field run on the per-body kernel. */
 H2O_API int h2o_set_surface_heights(h2o_handle h, const void* eta_dev);
 
 /* Dense added mass.  calculate_added_mass (numba_hydrodynamics.py:219-253) takes
