@@ -370,7 +370,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
     extern __shared__ __align__(128) unsigned char smem[];
 
     const int tid = threadIdx.x;
-    const int TB = a.tile_bodies;  // bodies per tile (<= kThreads)
+    // bodies per tile: whole robots (<= kThreads) in robot mode, else every lane has a body
+    static_assert(kThreads % 4 == 0, "a full tile must keep every bulk copy a 16-byte multiple");
+    const int TB = kRobot ? a.tile_bodies : kThreads;
     S* const table = reinterpret_cast<S*>(smem + SM::OFF_TABLE);
     unsigned char* const slot_map = smem + SM::OFF_TABLE + size_t(MAX_TABLE_TYPES) * N_COEFF * sizeof(S);
     S* const robot_acc = reinterpret_cast<S*>(smem + SM::OFF_ROBOT);
@@ -442,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
         const int cnt = TB;
         const long long tile_begin = next_begin;
         next_begin += round_stride;
-        const bool active = tid < cnt;
+        const bool active = kRobot ? tid < cnt : true;
         const int robots_in_tile = kRobot ? cnt / bpr : 0;
         mbar_wait(&full_bar[stage], (it / kStagesIn) & 1);
 
