@@ -182,10 +182,14 @@ class HydroEngine:
             self._h, arr.ctypes.data_as(ctypes.c_void_p), L.H2O_F32 if arr.dtype == np.float32 else L.H2O_F64,
             _stream_ptr(self.device)))
 
+    def set_globals(self, water_density: float, gravity: float):
+        """waterDensity / gravity (hydrodynamics_behavior.py:30-31)."""
+        L.check(self._lib.h2o_set_globals(self._h, float(water_density), float(gravity)))
+        self.water_density, self.gravity = float(water_density), float(gravity)
+
     def set_workload_params(self, wl):
         """Configure from a ``workloads.Workload`` (globals, coefficients, articulation)."""
-        L.check(self._lib.h2o_set_globals(self._h, wl.rho, wl.g))
-        self.water_density, self.gravity = wl.rho, wl.g
+        self.set_globals(wl.rho, wl.g)
         if wl.coeff is not None:
             self.set_params_per_body(wl.coeff)
         else:
