@@ -129,9 +129,10 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 // ---------------------------------------------------------------------------
 // T bodies per tile (= threads per CTA), I-deep TMA load ring, O store buffers,
 // MB = minimum CTAs per SM promised to the compiler (register budget).
-template <int T, int I, int O, int MB, bool CO = false> struct Cfg {
+template <int T, int I, int O, int MB, bool CO = false, int BPR = 0> struct Cfg {
     static constexpr int kThreads = T, kIn = I, kOut = O, kMinBlocks = MB;
     static constexpr bool kCopyOnly = CO;  // measurement aid: memory traffic without arithmetic
+    static constexpr int kBpr = BPR;       // robot mode specialised for this robot size (0 = run time)
 };
 template <typename S> struct DefaultCfg;
 template <> struct DefaultCfg<float> { using type = Cfg<128, 1, 2, 6>; };
@@ -139,16 +140,20 @@ template <> struct DefaultCfg<double> { using type = Cfg<64, 1, 2, 6>; };
 // With an articulation a tile holds whole robots (and whole 16-byte granules), e.g. 19-body
 // hexapods -> multiples of 76 bodies.  Several CTA sizes are compiled and the one whose lanes are
 // best used is picked per bodies_per_robot (19: 160 threads carry 152 bodies = 95 %).
+// the reference's robot: SILVER2 = Body + 6 x (Coxa, Femur, Tibia) scripted prims
+constexpr int HEXAPOD_BODIES = 19;
 template <typename S> struct RobotCfgs;
 template <> struct RobotCfgs<float> {
     using A = Cfg<128, 1, 2, 6>;
     using B = Cfg<160, 1, 2, 4>;
     using C = Cfg<256, 1, 2, 3>;
+    using Hexapod = Cfg<160, 1, 2, 4, false, HEXAPOD_BODIES>;  // = B with the robot size compiled in
 };
 template <> struct RobotCfgs<double> {
     using A = Cfg<64, 1, 2, 6>;
     using B = Cfg<96, 1, 2, 4>;
     using C = Cfg<160, 1, 2, 2>;
+    using Hexapod = Cfg<160, 1, 2, 2, false, HEXAPOD_BODIES>;  // = C with the robot size compiled in
 };
 
 template <typename S, int kLayout, int kParam, bool kRobot, bool kStats, typename C> struct TileLaunch {
@@ -156,7 +161,7 @@ template <typename S, int kLayout, int kParam, bool kRobot, bool kStats, typenam
     static auto kernel()
     {
         return &step_tile_kernel<S, kLayout, kParam, kRobot, kStats, C::kThreads, C::kIn, C::kOut, C::kMinBlocks,
-                                 C::kCopyOnly>;
+                                 C::kCopyOnly, C::kBpr>;
     }
     static size_t smem() { return SM::total(kRobot); }
     static cudaError_t prepare(int* ctas_per_sm)
@@ -200,6 +205,10 @@ static int launch_tile(h2o_engine* e, StepArgs& a, cudaStream_t stream)
         ctas_per_sm[dev] = c;
     }
     const int tb_max = tile_bodies_for(C::kThreads, sizeof(S), kRobot ? a.bodies_per_robot : 0);
+    if (C::kBpr > 0 && (a.bodies_per_robot != C::kBpr ||
+                        tb_max != tile_bodies_static(C::kThreads, int(sizeof(S)), C::kBpr > 0 ? C::kBpr : 1)))
+        return fail(H2O_ERR_BAD_ARGUMENT, "kernel specialised for %d-body robots launched with %d", C::kBpr,
+                    a.bodies_per_robot);
     int cps = ctas_per_sm[dev];
     if (e->max_ctas_per_sm > 0) cps = std::min(cps, e->max_ctas_per_sm);
     const long long slots = (long long)e->sm_count * cps;
@@ -323,7 +332,9 @@ static int step_typed2(h2o_engine* e, StepArgs& a, cudaStream_t stream)
                 const double uc = double(tile_bodies_for(RC::C::kThreads, sizeof(S), bpr)) / RC::C::kThreads;
                 int pick = (ua >= ub - 0.03 && ua >= uc - 0.06) ? 0 : (ub >= uc - 0.03 ? 1 : 2);
                 if (e->robot_cfg >= 0) pick = e->robot_cfg;
-                if (pick == 0) rc = launch_tile<S, kLayout, kParam, true, kStats, typename RC::A>(e, a, stream);
+                if (bpr == HEXAPOD_BODIES && e->robot_cfg < 0)
+                    rc = launch_tile<S, kLayout, kParam, true, kStats, typename RC::Hexapod>(e, a, stream);
+                else if (pick == 0) rc = launch_tile<S, kLayout, kParam, true, kStats, typename RC::A>(e, a, stream);
                 else if (pick == 1) rc = launch_tile<S, kLayout, kParam, true, kStats, typename RC::B>(e, a, stream);
                 else rc = launch_tile<S, kLayout, kParam, true, kStats, typename RC::C>(e, a, stream);
             }

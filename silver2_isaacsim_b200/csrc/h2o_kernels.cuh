@@ -361,8 +361,20 @@ struct TileSmem {
 // next tile's loads with this tile's compute, which keeps shared memory per CTA small and
 // lets many CTAs share an SM (the kernel is issue-bound, so resident warps matter).
 // ---------------------------------------------------------------------------
+// Bodies per tile when the robot size is a compile-time constant: whole robots AND whole 16-byte
+// granules (4 fp32 / 2 fp64 bodies), as many as fit the CTA.  Mirrors tile_bodies_for() on the host.
+constexpr int tile_gcd(int a, int b) { return b ? tile_gcd(b, a % b) : a; }
+constexpr int tile_bodies_static(int threads, int esz, int bpr)
+{
+    const int granule = 16 / esz;
+    const int unit = granule / tile_gcd(granule, bpr) * bpr;
+    return threads / unit * unit;
+}
+
+// kBpr > 0 specialises robot mode for one robot size (19 = the SILVER2 hexapod): tile size, robot index
+// and the per-robot sums become compile-time (-8 % time on the C4 shard); 0 = any size at run time.
 template <typename S, int kLayout, int kParam, bool kRobot, bool kStats, int kThreads, int kStagesIn,
-          int kStagesOut, int kMinBlocks, bool kCopyOnly = false>
+          int kStagesOut, int kMinBlocks, bool kCopyOnly = false, int kBpr = 0>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const __grid_constant__ StepArgs a)
 {
     using TL = TileLayout<S, kLayout, kParam>;
@@ -372,7 +384,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
     const int tid = threadIdx.x;
     // bodies per tile: whole robots (<= kThreads) in robot mode, else every lane has a body
     static_assert(kThreads % 4 == 0, "a full tile must keep every bulk copy a 16-byte multiple");
-    const int TB = kRobot ? a.tile_bodies : kThreads;
+    static_assert(kBpr == 0 || kRobot, "kBpr only applies to robot mode");
+    const int TB = kRobot ? (kBpr > 0 ? tile_bodies_static(kThreads, int(sizeof(S)), kBpr > 0 ? kBpr : 1) : a.tile_bodies) : kThreads;
     S* const table = reinterpret_cast<S*>(smem + SM::OFF_TABLE);
     unsigned char* const slot_map = smem + SM::OFF_TABLE + size_t(MAX_TABLE_TYPES) * N_COEFF * sizeof(S);
     S* const robot_acc = reinterpret_cast<S*>(smem + SM::OFF_ROBOT);
@@ -435,7 +448,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
     ThreadStats st;
     const S inv_dt = S(a.inv_dt);
     const Env env{a.current[0], a.current[1], a.current[2], a.surface_z};
-    const int bpr = a.bodies_per_robot;
+    const int bpr = kBpr > 0 ? kBpr : a.bodies_per_robot;
 
     long long next_begin = first_begin;
     for (int it = 0; it < n_it; ++it) {
@@ -532,22 +545,25 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
             bulk_s2g(reinterpret_cast<S*>(a.prev) + tile_begin * 6, out + oo_prev, cb * 6);
             bulk_commit();
         }
-        if (kRobot && tid < robots_in_tile * 6) {
+        if (kRobot) {
             // Per-robot net wrench: thread (robot, component) sums its robot's bodies straight out of
             // shared memory in body order (deterministic; bank-conflict free for the strides involved).
             // Measured on the C4 shard (profiles/r01_robot_wrench_variants.log): segmented warp-shuffle
             // scan over all lanes + shared-memory atomics 80 us, this 68 us, lane pairs + shuffle 72 us.
             // The scratch is rewritten only after the next tile's barrier (A), which these threads
             // reach after the sum.  (robot_wrench_kernel -- tails, robots larger than a tile -- reduces
-            // one robot per warp with shuffles.)
-            const int rb = tid / 6, c = tid - 6 * rb;
-            const S* src = (c < 3) ? reinterpret_cast<const S*>(out) + 3 * (rb * bpr) + c
-                                   : robot_acc + (c - 3) * TB + rb * bpr;
-            const int step = (c < 3) ? 3 : 1;
-            S sum = S(0);
+            // one robot per warp with shuffles.)  Robots of fewer than 6 bodies have more (robot,
+            // component) sums than the tile has threads, hence the stride loop.
+            for (int idx = tid; idx < robots_in_tile * 6; idx += kThreads) {
+                const int rb = idx / 6, c = idx - 6 * rb;
+                const S* src = (c < 3) ? reinterpret_cast<const S*>(out) + 3 * (rb * bpr) + c
+                                       : robot_acc + (c - 3) * TB + rb * bpr;
+                const int step = (c < 3) ? 3 : 1;
+                S sum = S(0);
 #pragma unroll 4
-            for (int j = 0; j < bpr; ++j) sum += src[j * step];
-            reinterpret_cast<S*>(a.out_wrench)[(tile_begin / bpr) * 6 + tid] = sum;
+                for (int j = 0; j < bpr; ++j) sum += src[j * step];
+                reinterpret_cast<S*>(a.out_wrench)[(tile_begin / bpr) * 6 + idx] = sum;
+            }
         }
     }
     if (tid == 0) bulk_wait_all<0>();

@@ -101,6 +101,31 @@ def test_step_hexapod_table_and_robot_wrench(oracle, dev, dtype, kernel):
     assert (err <= tol + 1e-6).all(), float((err / (tol + 1e-6)).max())
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["fp32", "fp64"])
+@pytest.mark.parametrize("bpr", [1, 2, 4, 5, 7, 12, 32, 45])
+def test_robot_wrench_any_robot_size(oracle, dev, bpr, dtype):
+    """The 19-body hexapod has a compiled-in robot size; every other size takes the run-time path
+    (whole-robot tiles sized per bodies_per_robot; robots of < 6 bodies have more sums than threads)
+    and must give the same per-robot sums."""
+    n_robots = 48_000 // bpr + 3
+    wl = W.heterogeneous_boxes(n_robots * bpr, seed=500 + bpr, xy_range=2.0)
+    e = _engine(wl, dtype, dev, "tile")
+    e.set_articulation(bpr)
+    F, T, Wr = _run_step(e, wl, dtype, dev, "split", robot=True)
+    assert e.last_kernel == "tile"
+    ref = _ref(oracle, wl)
+    if dtype == torch.float32:
+        scoring.assert_fp32(F, ref.force, f"robots of {bpr} force", min_pass=0.9999)
+        scoring.assert_fp32(T, ref.torque, f"robots of {bpr} torque", min_pass=0.9999)
+    else:
+        _check(wl, dtype, ref, F, T, f"robots of {bpr}")
+    want = oracle.robot_wrench(wl.pos, ref.force, ref.torque, bpr)
+    mag = oracle.robot_wrench(wl.pos, np.abs(ref.force), np.abs(ref.torque), bpr)
+    err, _ = scoring.vec_err(Wr, want)
+    tol = (1e-5 if dtype == torch.float32 else 1e-11) * np.abs(mag).max(axis=1) * 20
+    assert (err <= tol + 1e-6).all(), float((err / (tol + 1e-6)).max())
+
+
 def test_step_sharded_robots_per_body_records(oracle, dev):
     """C4 shard: heterogeneous per-robot jitter (per-body records) + robot wrench, PhysX layout."""
     wl = W.sharded_robots(4099)
