@@ -126,6 +126,32 @@ def test_robot_wrench_any_robot_size(oracle, dev, bpr, dtype):
     assert (err <= tol + 1e-6).all(), float((err / (tol + 1e-6)).max())
 
 
+@pytest.mark.parametrize("kernel", ["tile", "direct"])
+@pytest.mark.parametrize("n_slots,n_types", [(1, 1), (3, 2), (7, 4), (64, 16), (200, 5)])
+def test_part_table_any_slot_map(oracle, dev, kernel, n_slots, n_types):
+    """Part-type table mode with arbitrary slot maps (body i -> table[slot_type[i % n_slots]]): the
+    slot phase must survive tile boundaries and the direct-kernel tail for any n_slots, not just 19."""
+    from silver2_isaacsim_b200 import HydroEngine, params as P
+
+    n = 50_003
+    wl = W.heterogeneous_boxes(n, seed=900 + n_slots)
+    rng = np.random.default_rng(n_slots)
+    table = np.asarray(wl.coeff, dtype=np.float64)[rng.choice(n, n_types, replace=False)]
+    slots = rng.integers(0, n_types, n_slots).astype(np.int32)
+    slots[:min(n_slots, n_types)] = np.arange(min(n_slots, n_types))
+    coeff = table[slots[np.arange(n) % n_slots]]
+    e = HydroEngine(n, device=dev)
+    e.set_globals(wl.rho, wl.g)
+    e.set_part_table(table, slots)
+    e.set_kernel(kernel)
+    F, T = _run_step(e, wl, torch.float32, dev)
+    assert e.last_kernel == kernel
+    ref = oracle.step(P.coeff_to_ctor_rows(coeff, wl.rho, wl.g), coeff[:, 10].copy(), wl.pos, wl.quat_xyzw,
+                      wl.lin_vel, wl.ang_vel, wl.prev_lin, wl.prev_ang, wl.dt)
+    scoring.assert_fp32(F, ref.force, "table force", min_pass=0.9999)
+    scoring.assert_fp32(T, ref.torque, "table torque", min_pass=0.9999)
+
+
 def test_step_sharded_robots_per_body_records(oracle, dev):
     """C4 shard: heterogeneous per-robot jitter (per-body records) + robot wrench, PhysX layout."""
     wl = W.sharded_robots(4099)
@@ -288,6 +314,34 @@ def test_step_host_pipeline(oracle, dev):
     e3.step_host(*pin, wl.dt, out_force=oF, out_torque=oT)
     for x, y in ((oF.numpy(), F), (oT.numpy(), T)):  # different chunking (no robot tiles) -> rounding-level
         assert scoring.fp32_ok(x, y, rel=2e-6).mean() > 0.999 and scoring.fp32_ok(x, y, rel=1e-4).all()
+
+
+def test_step_host_table_slots_and_height_field(oracle, dev):
+    """Host pipeline chunking keeps the slot phase of a part table (n_slots does not divide the chunk
+    size) and offsets a borrowed per-body height field per chunk."""
+    from silver2_isaacsim_b200 import HydroEngine, params as P
+
+    n, n_slots, n_types = 300_007, 7, 3
+    wl = W.heterogeneous_boxes(n, seed=4242)
+    rng = np.random.default_rng(7)
+    table = np.asarray(wl.coeff, dtype=np.float64)[rng.choice(n, n_types, replace=False)]
+    slots = np.array([0, 1, 2, 1, 0, 2, 2], dtype=np.int32)
+    coeff = table[slots[np.arange(n) % n_slots]]
+    eta = (0.2 * np.sin(0.5 * wl.pos[:, 0].astype(np.float64))).astype(np.float32)
+    ctor, mass = P.coeff_to_ctor_rows(coeff, wl.rho, wl.g), coeff[:, 10].copy()
+    for use_eta in (False, True):
+        e = HydroEngine(n, device=dev)
+        e.set_globals(wl.rho, wl.g)
+        e.set_part_table(table, slots)
+        e.set_prev(_t(wl.prev_lin, torch.float32, dev), _t(wl.prev_ang, torch.float32, dev))
+        pos = wl.pos.astype(np.float64).copy()
+        if use_eta:
+            e.set_surface_heights(torch.as_tensor(eta, device=dev))
+            pos[:, 2] -= eta.astype(np.float64)
+        F, T = e.step_host(wl.pos, wl.quat_xyzw, wl.lin_vel, wl.ang_vel, wl.dt)
+        ref = oracle.step(ctor, mass, pos, wl.quat_xyzw, wl.lin_vel, wl.ang_vel, wl.prev_lin, wl.prev_ang, wl.dt)
+        scoring.assert_fp32(F, ref.force, f"step_host table eta={use_eta} force", min_pass=0.9999)
+        scoring.assert_fp32(T, ref.torque, f"step_host table eta={use_eta} torque", min_pass=0.9999)
 
 
 def test_stats_vector(oracle, dev):
