@@ -344,6 +344,46 @@ def test_step_host_table_slots_and_height_field(oracle, dev):
         scoring.assert_fp32(T, ref.torque, f"step_host table eta={use_eta} torque", min_pass=0.9999)
 
 
+def test_unaligned_views_are_refused(dev):
+    """The boundary requires 16-byte aligned tensors (include/h2o.h): contiguous views with a 12-byte
+    offset are refused with H2O_ERR_ALIGNMENT by the DLPack and the raw-pointer entry points alike."""
+    import ctypes
+    from silver2_isaacsim_b200 import _lib as L
+
+    wl = W.heterogeneous_boxes(4096, seed=31)
+    e = _engine(wl, torch.float32, dev)
+    pad = lambda a: torch.cat([torch.zeros(1, a.shape[1], device=dev), _t(a, torch.float32, dev)])[1:]
+    pos, quat, lin, ang = pad(wl.pos), _t(wl.quat_xyzw, torch.float32, dev), pad(wl.lin_vel), pad(wl.ang_vel)
+    assert pos.is_contiguous() and pos.data_ptr() % 16 != 0
+    with pytest.raises(L.H2OError, match="ALIGNMENT"):
+        e.step(pos, quat, lin, ang, wl.dt)
+    F, T = torch.empty(wl.n, 3, device=dev), torch.empty(wl.n, 3, device=dev)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    rc = e._lib.h2o_step(e._h, p(pos), p(quat), p(lin), p(ang), ctypes.c_double(wl.dt), p(F), p(T), None,
+                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 7  # H2O_ERR_ALIGNMENT (include/h2o.h)
+
+
+def test_graph_rollout_with_robot_wrench(oracle, dev):
+    """A captured rollout over bound tensors carries the per-robot wrench output too."""
+    wl = W.hexapod_envs(4096)
+    e = _engine(wl, torch.float32, dev)
+    ten = [_t(a, torch.float32, dev) for a in (wl.pos, wl.quat_xyzw, wl.lin_vel, wl.ang_vel)]
+    F, T, Wr = e.bind(*ten, robot_wrench=True)
+    e.capture_rollout(3, wl.dt)      # one eager step, then the 3 captured ones
+    Wr.fill_(777.0)
+    e.launch_rollout()
+    torch.cuda.synchronize()
+    # static state: from the second step on v_prev == v, so the steady answer has zero acceleration
+    ref = oracle.step(wl.ctor_rows(), wl.masses(), wl.pos, wl.quat_xyzw, wl.lin_vel, wl.ang_vel,
+                      wl.lin_vel.copy(), wl.ang_vel.copy(), wl.dt)
+    _check(wl, torch.float32, ref, F.double().cpu().numpy(), T.double().cpu().numpy(), "graph rollout robots")
+    want = oracle.robot_wrench(wl.pos, ref.force, ref.torque, 19)
+    mag = oracle.robot_wrench(wl.pos, np.abs(ref.force), np.abs(ref.torque), 19)
+    err, _ = scoring.vec_err(Wr.double().cpu().numpy(), want)
+    assert (err <= 2e-4 * np.abs(mag).max(axis=1) + 1e-6).all()
+
+
 def test_stats_vector(oracle, dev):
     wl = W.heterogeneous_boxes(70_001, seed=11)
     ref = _ref(oracle, wl)
