@@ -400,6 +400,24 @@ def test_stats_vector(oracle, dev):
         assert e.stats()["bodies"] == 0
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["fp32", "fp64"])
+def test_stats_vector_with_robot_tiles(oracle, dev, dtype):
+    """Statistics through the whole-robot tile kernels (hexapod-specialised and run-time robot size),
+    table parameters; robots whose tail goes through the per-body kernel are counted once."""
+    for wl, bpr in ((W.hexapod_envs(4099), 19), (W.heterogeneous_boxes(7 * 9001, seed=12, xy_range=2.0), 7)):
+        ref = _ref(oracle, wl)
+        e = _engine(wl, dtype, dev, "tile", stats=True)
+        e.set_articulation(bpr)
+        _run_step(e, wl, dtype, dev, robot=True)
+        assert e.last_kernel == "tile"
+        s = e.stats(reset=True)
+        assert s["bodies"] == wl.n and s["nonfinite_bodies"] == 0
+        assert s["wet_bodies"] == int((ref.components["sub_ratio"] > 0).sum())
+        norms = np.linalg.norm(ref.force, axis=1)
+        assert s["sum_force_norm"] == pytest.approx(norms.sum(), rel=1e-6)
+        assert s["max_force_norm"] == pytest.approx(norms.max(), rel=1e-6)
+
+
 # --------------------------------------------------------------------------- error behaviour
 def test_error_codes(dev):
     from silver2_isaacsim_b200 import H2OError, HydroEngine
