@@ -560,8 +560,16 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
                                        : robot_acc + (c - 3) * TB + rb * bpr;
                 const int step = (c < 3) ? 3 : 1;
                 S sum = S(0);
+                if (kBpr > 0) {  // loads first, then the adds in body order
+                    S v[kBpr > 0 ? kBpr : 1];
+#pragma unroll
+                    for (int j = 0; j < kBpr; ++j) v[j] = src[j * step];
+#pragma unroll
+                    for (int j = 0; j < kBpr; ++j) sum += v[j];
+                } else {
 #pragma unroll 4
-                for (int j = 0; j < bpr; ++j) sum += src[j * step];
+                    for (int j = 0; j < bpr; ++j) sum += src[j * step];
+                }
                 reinterpret_cast<S*>(a.out_wrench)[(tile_begin / bpr) * 6 + idx] = sum;
             }
         }
