@@ -543,6 +543,7 @@ int h2o_set_part_table(h2o_handle h, int n_types, const double* table_host, int 
     DeviceGuard g(e->device);
     if (e->coeff) { cudaFree(e->coeff); e->coeff = nullptr; }
     if (e->slot_type) { cudaFree(e->slot_type); e->slot_type = nullptr; }
+    e->param_mode = -1;  // not configured until the uploads below succeed
     const size_t cnt = size_t(n_types) * N_COEFF;
     CUDA_TRY(cudaMalloc(&e->coeff, cnt * e->esz));
     CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&e->slot_type), n_slots * sizeof(int32_t)));
@@ -630,6 +631,7 @@ int h2o_set_params_per_body(h2o_handle h, const void* coeff, int src_dtype, h2o_
     const size_t cnt = size_t(e->n) * N_COEFF;
     if (e->param_mode != PARAM_PER_BODY) {
         if (e->coeff) { cudaFree(e->coeff); e->coeff = nullptr; }
+        e->param_mode = -1;  // not configured until the upload below succeeds
         CUDA_TRY(cudaMalloc(&e->coeff, cnt * e->esz));
     }
     if (src_dtype == e->dtype) {
