@@ -464,14 +464,16 @@ int h2o_create(h2o_handle* out, int64_t n_bodies, int dtype, int device)
     if (const char* v = getenv("H2O_PDL")) e->use_pdl = atoi(v) != 0;
     if (const char* v = getenv("H2O_ROBOT_CFG")) e->robot_cfg = std::max(-1, std::min(2, atoi(v)));
     if (cudaMalloc(&e->prev, size_t(n_bodies) * 6 * e->esz) != cudaSuccess ||
-        cudaMalloc(reinterpret_cast<void**>(&e->stats), N_STATS * sizeof(double)) != cudaSuccess) {
-        cudaGetLastError();
+        cudaMalloc(reinterpret_cast<void**>(&e->stats), N_STATS * sizeof(double)) != cudaSuccess ||
+        cudaMemset(e->prev, 0, size_t(n_bodies) * 6 * e->esz) != cudaSuccess ||
+        cudaMemset(e->stats, 0, N_STATS * sizeof(double)) != cudaSuccess) {
+        const cudaError_t why = cudaGetLastError();
         if (e->prev) cudaFree(e->prev);
+        if (e->stats) cudaFree(e->stats);
         delete e;
-        return fail(H2O_ERR_CUDA, "cudaMalloc of engine state failed");
+        return fail(H2O_ERR_CUDA, "allocating the engine state for %lld bodies failed: %s", (long long)n_bodies,
+                    cudaGetErrorString(why));
     }
-    CUDA_TRY(cudaMemset(e->prev, 0, size_t(n_bodies) * 6 * e->esz));
-    CUDA_TRY(cudaMemset(e->stats, 0, N_STATS * sizeof(double)));
     *out = e;
     return H2O_OK;
 }
