@@ -34,3 +34,33 @@ for thr in (1, O.max_threads()):
         O.components(ctor, wl.pos, wl.quat_xyzw, wl.lin_vel, wl.ang_vel, a, al, n_threads=thr)
     el = time.perf_counter() - t
     print(f"C oracle port, {thr} thread(s): {20 * wl.n / el:.3g} updates/s")
+
+# (c) SURVEY.md 8(d) "CPU baseline (2)": a harness-side @njit(parallel=True) prange driver calling the
+# UNTOUCHED reference solve_hydrodynamics once per body (uniform README parameters so that one set of
+# geometry arrays serves every body; moving bodies only -- a wet body at rest raises).
+import numba
+from numba import njit, prange
+_, solve = ref_numba.load()
+wref = Wrapper(1, 1, 1, 1.2, 0.8, 300, 150, 1025, 9.81, 0.05, 0.02, 1.0)
+geom = (wref._local_keypoints, wref._local_face_centers, wref._face_areas, wref._local_face_normals, wref._added_mass_matrix)
+
+@njit(parallel=True)
+def drive(pos, quat, v, w, a, al, kp, fc, fa, fn, am, out):
+    for i in prange(pos.shape[0]):
+        r = solve(pos[i], quat[i], v[i], w[i], a[i], al[i], 1.0, 1025.0, 9.81, 1.2, 0.8, 300.0, 150.0, 1.0, kp, fc, fa, fn, am)
+        out[i, 0:3] = r[0] + r[1] + r[2] + r[4]
+        out[i, 3:6] = r[3] + r[5]
+
+n = 200000
+big = W.heterogeneous_boxes(n)
+f8 = lambda x: np.ascontiguousarray(x, dtype=np.float64)
+args2 = [f8(big.pos), f8(big.quat_xyzw), f8(big.lin_vel), f8(big.ang_vel),
+         f8((big.lin_vel.astype(np.float64) - big.prev_lin) / big.dt), f8((big.ang_vel.astype(np.float64) - big.prev_ang) / big.dt)]
+out = np.zeros((n, 6))
+drive(*[x[:64] for x in args2], *geom, out[:64])  # JIT
+for thr in (1, numba.get_num_threads()):
+    numba.set_num_threads(thr)
+    best = 1e9
+    for _ in range(3):
+        t = time.perf_counter(); drive(*args2, *geom, out); best = min(best, time.perf_counter() - t)
+    print(f"reference solve_hydrodynamics in a prange driver, {thr} thread(s): {n / best:.3g} updates/s ({best / n * 1e6:.2f} us/body)")
