@@ -252,6 +252,41 @@ struct ThreadStats {
     unsigned wet = 0, clamped = 0, nonfinite = 0, still = 0, bodies = 0;
 };
 
+// fp32 mode, quaternion further from unit than fast_path_valid() allows: out-of-line world-frame
+// evaluation (exact in dq, like fp64 mode), so that fp32 mode follows the reference for ANY q.
+// Everything crosses the call by value, so the fast path keeps its registers.
+struct GeneralStepOut {
+    float F[3], T[3];
+    float ratio;
+    int flags;  // bit 0 clamped, bit 1 still
+};
+__device__ __noinline__ GeneralStepOut body_step_general_f32(
+    double pz, double qx, double qy, double qz, double qw, float vx, float vy, float vz, float wx, float wy, float wz,
+    float ax, float ay, float az, float bx, float by, float bz, float dimx, float dimy, float dimz, float c_drag,
+    float c_drag_ang, float k_damp, float k_damp_ang, float c_am, float c_am_ang, float c_lift, float mass,
+    double rho, double grav, const float* am_dense)
+{
+    BodyIn<double, float> g;
+    g.pz = pz; g.qx = qx; g.qy = qy; g.qz = qz; g.qw = qw;
+    g.vx = vx; g.vy = vy; g.vz = vz; g.wx = wx; g.wy = wy; g.wz = wz;
+    g.ax = ax; g.ay = ay; g.az = az; g.bx = bx; g.by = by; g.bz = bz;
+    g.acc_scale = 1.0f;
+    g.dimx = dimx; g.dimy = dimy; g.dimz = dimz;
+    g.c_drag = c_drag; g.c_drag_ang = c_drag_ang; g.k_damp = k_damp; g.k_damp_ang = k_damp_ang;
+    g.c_am = c_am; g.c_am_ang = c_am_ang; g.c_lift = c_lift;
+    g.warp_compat = false;
+    g.rho_h = rho; g.grav_h = grav; g.rho = float(rho);
+    g.am_dense = am_dense;
+    Terms<double, float> t;
+    body_terms<double, float, false>(g, t);
+    GeneralStepOut o;
+    bool clamped;
+    net_wrench<double, float>(t, mass, o.F, o.T, clamped);
+    o.ratio = float(t.ratio);
+    o.flags = (clamped ? 1 : 0) | (t.still ? 2 : 0);
+    return o;
+}
+
 // fp32 mode: body-frame fast path; fp64 mode: the world-frame formulation (exact in dq).
 template <typename S>
 __device__ __forceinline__ void body_step(const BodyIn<double, S>& in, S mass, S F[3], S T[3],
@@ -260,7 +295,24 @@ __device__ __forceinline__ void body_step(const BodyIn<double, S>& in, S mass, S
     bool clamped, still;
     double ratio;
     if (sizeof(S) == 4) {
-        body_wrench_fast<double, S>(in, mass, F, T, clamped, ratio, still);
+        if (!fast_path_valid(in)) {
+            const float sc = float(in.acc_scale);
+            const GeneralStepOut o = body_step_general_f32(
+                in.pz, in.qx, in.qy, in.qz, in.qw, float(in.vx), float(in.vy), float(in.vz), float(in.wx), float(in.wy),
+                float(in.wz), float(in.ax) * sc, float(in.ay) * sc, float(in.az) * sc, float(in.bx) * sc,
+                float(in.by) * sc, float(in.bz) * sc, float(in.dimx), float(in.dimy), float(in.dimz), float(in.c_drag),
+                float(in.c_drag_ang), float(in.k_damp), float(in.k_damp_ang), float(in.c_am), float(in.c_am_ang),
+                float(in.c_lift), float(mass), in.rho_h, in.grav_h, reinterpret_cast<const float*>(in.am_dense));
+            for (int k = 0; k < 3; ++k) {
+                F[k] = S(o.F[k]);
+                T[k] = S(o.T[k]);
+            }
+            ratio = double(o.ratio);
+            clamped = (o.flags & 1) != 0;
+            still = (o.flags & 2) != 0;
+        } else {
+            body_wrench_fast<double, S>(in, mass, F, T, clamped, ratio, still);
+        }
     } else {
         Terms<double, S> t;
         body_terms<double, S, false>(in, t);

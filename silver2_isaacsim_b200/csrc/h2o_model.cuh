@@ -185,6 +185,16 @@ template <typename H, typename L> struct BodyIn {
                           // wrapper's diagonal built from c_am / c_am_ang (wrapper :101-112)
 };
 
+// The body-frame fast path (body_wrench_fast) treats R(q) as orthogonal.  The reference never normalises
+// q, so its R is orthogonal only up to dq = |q|^2 - 1.  Quaternions handed out by a simulator are unit to
+// fp32 rounding (|dq| <= 2.4e-7); anything further from unit must take body_terms + net_wrench (exact in dq).
+constexpr double FAST_PATH_MAX_DQ = 1e-6;
+template <typename H, typename L> H2O_HD bool fast_path_valid(const BodyIn<H, L>& in)
+{
+    const H dq = ((in.qx * in.qx + in.qy * in.qy) + (in.qz * in.qz + in.qw * in.qw)) - H(1);
+    return !(h2o_abs(dq) > H(FAST_PATH_MAX_DQ));
+}
+
 template <typename H, typename L> struct Terms {
     H ratio;              // submersion ratio (0 => every other field is 0)
     H fbz;                // buoyancy force, +z (numba_hydrodynamics.py:282)

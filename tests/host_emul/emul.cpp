@@ -52,12 +52,19 @@ static void run(int64_t n, const double* pos, const double* quat, const double* 
         Terms<H, L> t;
         L f[3], tq[3];
         bool clamped;
-        if (kFast) {
+        if (kFast && fast_path_valid(in)) {
             H ratio;
             bool still;
             body_wrench_fast<H, L>(in, L(S(c[10])), f, tq, clamped, ratio, still);
             comp = nullptr;
             t.kp_mask = 0;
+        } else if (kFast) {  // same dispatch as body_step() in h2o_kernels.cuh
+            in.ax *= in.acc_scale; in.ay *= in.acc_scale; in.az *= in.acc_scale;
+            in.bx *= in.acc_scale; in.by *= in.acc_scale; in.bz *= in.acc_scale;
+            in.acc_scale = L(1);
+            body_terms<H, L, false>(in, t);
+            net_wrench<H, L>(t, L(S(c[10])), f, tq, clamped);
+            comp = nullptr;
         } else {
             body_terms<H, L, kExactTrig>(in, t);
             net_wrench<H, L>(t, L(S(c[10])), f, tq, clamped);
