@@ -123,6 +123,13 @@ H2O_API int h2o_set_part_table(h2o_handle h, int n_types, const double* table_ho
  * src_dtype H2O_F32/H2O_F64 (converted to the handle dtype on the device). */
 H2O_API int h2o_set_params_per_body(h2o_handle h, const void* coeff, int src_dtype, h2o_stream stream);
 
+/* Same, struct-of-arrays: cols[k] is a DEVICE array (n_bodies,) holding coefficient k of every body, in
+ * H2O_N_COEFF order (xDimension, yDimension, zDimension, linearDragCoefficient, angularDragCoefficient,
+ * linearDamping, angularDamping, linearAddedMassCoefficient, angularAddedMassCoefficient,
+ * liftCoefficient -- the per-prim exposed variables of hydrodynamics_behavior.py:32-44 -- and mass, the
+ * one _setup reads from the view, :172-174).  Interleaved into the engine's records on the device. */
+H2O_API int h2o_set_params_soa(h2o_handle h, const void* const cols[11], int src_dtype, h2o_stream stream);
+
 /* Articulation structure: bodies are grouped in contiguous runs of bodies_per_robot;
  * 0 disables the per-robot wrench. */
 H2O_API int h2o_set_articulation(h2o_handle h, int bodies_per_robot);

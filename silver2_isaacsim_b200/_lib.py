@@ -53,6 +53,7 @@ SIGNATURES = {
     "h2o_set_params_uniform": (c_int, [_P, POINTER(c_double), c_double]),
     "h2o_set_part_table": (c_int, [_P, c_int, POINTER(c_double), c_int, POINTER(c_int32)]),
     "h2o_set_params_per_body": (c_int, [_P, _P, c_int, _P]),
+    "h2o_set_params_soa": (c_int, [_P, POINTER(c_void_p), c_int, _P]),
     "h2o_set_articulation": (c_int, [_P, c_int]),
     "h2o_set_quat_order": (c_int, [_P, c_int]),
     "h2o_set_kernel": (c_int, [_P, c_int]),

@@ -665,6 +665,50 @@ int h2o_set_params_per_body(h2o_handle h, const void* coeff, int src_dtype, h2o_
     return H2O_OK;
 }
 
+int h2o_set_params_soa(h2o_handle h, const void* const cols[11], int src_dtype, h2o_stream stream)
+{
+    h2o_engine* e = check(h);
+    if (!e) return H2O_ERR_BAD_HANDLE;
+    if (!cols) return fail(H2O_ERR_BAD_ARGUMENT, "cols is NULL");
+    if (src_dtype != H2O_F32 && src_dtype != H2O_F64) return fail(H2O_ERR_BAD_DTYPE, "bad src_dtype");
+    DeviceGuard g(e->device);
+    SoaCols sc;
+    for (int k = 0; k < N_COEFF; ++k) {
+        if (!cols[k]) return fail(H2O_ERR_BAD_ARGUMENT, "column %d is NULL", k);
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, cols[k]) != cudaSuccess ||
+            (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)) {
+            cudaGetLastError();
+            return fail(H2O_ERR_BAD_DEVICE, "column %d is not device memory", k);
+        }
+        if (at.type == cudaMemoryTypeDevice && at.device != e->device)
+            return fail(H2O_ERR_BAD_DEVICE, "column %d lives on device %d, handle on %d", k, at.device, e->device);
+        sc.col[k] = cols[k];
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t cnt = size_t(e->n) * N_COEFF;
+    if (e->param_mode != PARAM_PER_BODY) {
+        if (e->coeff) { cudaFree(e->coeff); e->coeff = nullptr; }
+        e->param_mode = -1;  // not configured until the upload below succeeds
+        CUDA_TRY(cudaMalloc(&e->coeff, cnt * e->esz));
+    }
+    const int grid = int((e->n + 255) / 256);
+    if (e->dtype == H2O_F32) {
+        if (src_dtype == H2O_F32) soa_to_records_kernel<float, float><<<grid, 256, 0, s>>>(static_cast<float*>(e->coeff), sc, e->n);
+        else soa_to_records_kernel<float, double><<<grid, 256, 0, s>>>(static_cast<float*>(e->coeff), sc, e->n);
+    } else {
+        if (src_dtype == H2O_F32) soa_to_records_kernel<double, float><<<grid, 256, 0, s>>>(static_cast<double*>(e->coeff), sc, e->n);
+        else soa_to_records_kernel<double, double><<<grid, 256, 0, s>>>(static_cast<double*>(e->coeff), sc, e->n);
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(s));
+    e->param_mode = PARAM_PER_BODY;
+    e->coeff_rows = e->n;
+    e->n_slots = 1;
+    e->n_types = 0;
+    return H2O_OK;
+}
+
 int h2o_set_articulation(h2o_handle h, int bodies_per_robot)
 {
     h2o_engine* e = check(h);

@@ -804,6 +804,16 @@ __global__ void cast_kernel(D* dst, const Sx* src, long long n)
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = D(src[i]);
 }
+// eleven (N,) columns -> (N,11) records (struct-of-arrays parameter upload)
+struct SoaCols { const void* col[N_COEFF]; };
+template <typename D, typename Sx>
+__global__ void soa_to_records_kernel(D* dst, const __grid_constant__ SoaCols cols, long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#pragma unroll
+    for (int k = 0; k < N_COEFF; ++k) dst[N_COEFF * i + k] = D(static_cast<const Sx*>(cols.col[k])[i]);
+}
 // (N,3)+(N,3) <-> (N,6)
 template <typename S> __global__ void pack_prev_kernel(S* prev, const S* lin, const S* ang, long long n)
 {

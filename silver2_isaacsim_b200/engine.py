@@ -182,6 +182,23 @@ class HydroEngine:
             self._h, arr.ctypes.data_as(ctypes.c_void_p), L.H2O_F32 if arr.dtype == np.float32 else L.H2O_F64,
             _stream_ptr(self.device)))
 
+    def set_params_soa(self, columns: Sequence[torch.Tensor]):
+        """Per-body parameters as eleven (n,) CUDA tensors in ``params.COEFF_FIELDS`` order (float32 or
+        float64, all the same dtype), e.g. one tensor per exposed USD attribute + the view's masses."""
+        if len(columns) != L.N_COEFF:
+            raise ValueError(f"expected {L.N_COEFF} columns ({', '.join(P.COEFF_FIELDS)})")
+        dt = columns[0].dtype
+        if dt not in _TORCH_DTYPES:
+            raise ValueError("columns must be float32 or float64")
+        cols = []
+        for k, c in enumerate(columns):
+            if c.dtype != dt or c.device != self.device or tuple(c.shape) != (self.n_bodies,) or not c.is_contiguous():
+                raise ValueError(f"column {k} ({P.COEFF_FIELDS[k]}): need a contiguous ({self.n_bodies},) {dt} tensor "
+                                 f"on {self.device}")
+            cols.append(c)
+        arr = (ctypes.c_void_p * L.N_COEFF)(*[c.data_ptr() for c in cols])
+        L.check(self._lib.h2o_set_params_soa(self._h, arr, _TORCH_DTYPES[dt], _stream_ptr(self.device)))
+
     def set_globals(self, water_density: float, gravity: float):
         """waterDensity / gravity (hydrodynamics_behavior.py:30-31)."""
         L.check(self._lib.h2o_set_globals(self._h, float(water_density), float(gravity)))

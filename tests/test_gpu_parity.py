@@ -183,6 +183,27 @@ def test_stress_distribution_gpu(oracle, dev, dtype, kernel):
         assert scoring.fp64_ok(T, ref.torque, scale, extra=pn).all()
 
 
+@pytest.mark.parametrize("src", [torch.float32, torch.float64], ids=["cols32", "cols64"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["fp32", "fp64"])
+def test_params_struct_of_arrays(oracle, dev, dtype, src):
+    """Eleven per-attribute columns give the same engine as the (N,11) record upload."""
+    from silver2_isaacsim_b200 import HydroEngine
+
+    wl = W.heterogeneous_boxes(50_001, seed=61)
+    coeff = np.asarray(wl.coeff, dtype=np.float64)
+    cols = [torch.as_tensor(np.ascontiguousarray(coeff[:, k]), device=dev).to(src).contiguous() for k in range(11)]
+    e = HydroEngine(wl.n, dtype=dtype, device=dev)
+    e.set_globals(wl.rho, wl.g)
+    e.set_params_soa(cols)
+    F, T = _run_step(e, wl, dtype, dev)
+    e2 = _engine(wl, dtype, dev)
+    F2, T2 = _run_step(e2, wl, dtype, dev)
+    assert np.array_equal(F, F2) and np.array_equal(T, T2)
+    _check(wl, dtype, _ref(oracle, wl), F, T, "soa params")
+    with pytest.raises(ValueError):
+        e.set_params_soa(cols[:10])
+
+
 def test_step_sharded_robots_per_body_records(oracle, dev):
     """C4 shard: heterogeneous per-robot jitter (per-body records) + robot wrench, PhysX layout."""
     wl = W.sharded_robots(4099)
