@@ -134,6 +134,14 @@ H2O_API int h2o_set_params_soa(h2o_handle h, const void* const cols[11], int src
  * 0 disables the per-robot wrench. */
 H2O_API int h2o_set_articulation(h2o_handle h, int bodies_per_robot);
 
+/* Articulation of UNEQUAL robots (e.g. the reference's main scene: one 19-link SILVER2 plus the Obsea
+ * buoy as a robot of its own): robot r owns bodies [offsets[r], offsets[r+1]); offsets is a host array
+ * of n_robots + 1 entries, offsets[0] = 0, offsets[n_robots] = n_bodies, strictly increasing.  The
+ * out_robot_wrench of the step calls is then (n_robots, 6), each wrench about its robot's first body,
+ * reduced from the written force / torque arrays after the force kernel.  h2o_set_articulation
+ * replaces it again.  Not available through h2o_step_host. */
+H2O_API int h2o_set_articulation_offsets(h2o_handle h, int64_t n_robots, const int64_t* offsets);
+
 /* Isaac core hands quaternions as wxyz and the reference permutes them
  * (hydrodynamics_behavior.py:194); the wrappers themselves take xyzw. */
 H2O_API int h2o_set_quat_order(h2o_handle h, int order);

@@ -55,6 +55,7 @@ SIGNATURES = {
     "h2o_set_params_per_body": (c_int, [_P, _P, c_int, _P]),
     "h2o_set_params_soa": (c_int, [_P, POINTER(c_void_p), c_int, _P]),
     "h2o_set_articulation": (c_int, [_P, c_int]),
+    "h2o_set_articulation_offsets": (c_int, [_P, c_int64, POINTER(c_int64)]),
     "h2o_set_quat_order": (c_int, [_P, c_int]),
     "h2o_set_kernel": (c_int, [_P, c_int]),
     "h2o_set_tile_config": (c_int, [_P, c_int]),

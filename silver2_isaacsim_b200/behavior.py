@@ -36,13 +36,15 @@ class BatchedHydrodynamicsBehavior:
 
     def __init__(self, prim_names: Sequence[str], view, device: str = "cuda:0",
                  config_path: Optional[str] = None, dtype: torch.dtype = torch.float32,
-                 bodies_per_robot: int = 0):
+                 bodies_per_robot: int = 0, robot_offsets: Optional[Sequence[int]] = None):
         self.prim_names = list(prim_names)
         self._view = view
         self._device = device
         self._dtype = dtype
         self._config_path = config_path
         self._bodies_per_robot = int(bodies_per_robot)
+        # robots of unequal size, e.g. [0, 19, 20] for one SILVER2 + the Obsea buoy (the main scene)
+        self._robot_offsets = None if robot_offsets is None else [int(o) for o in robot_offsets]
         self._engine: Optional[HydroEngine] = None
         self._F = self._T = None
         self.robot_wrench = None
@@ -93,12 +95,15 @@ class BatchedHydrodynamicsBehavior:
         self._engine = HydroEngine(n, dtype=self._dtype, device=self._device,
                                    water_density=first.waterDensity, gravity=first.gravity, quat_order="wxyz")
         self._engine.set_params_per_body(np.asarray(rows, dtype=np.float64))
-        self._engine.set_articulation(self._bodies_per_robot)
+        if self._robot_offsets is not None:
+            self._engine.set_articulation_offsets(self._robot_offsets)
+        else:
+            self._engine.set_articulation(self._bodies_per_robot)
         dev = self._engine.device
         self._F = torch.empty(n, 3, dtype=self._dtype, device=dev)
         self._T = torch.empty(n, 3, dtype=self._dtype, device=dev)
-        self.robot_wrench = (torch.empty(n // self._bodies_per_robot, 6, dtype=self._dtype, device=dev)
-                             if self._bodies_per_robot > 0 else None)
+        self.robot_wrench = (torch.empty(self._engine.n_robots, 6, dtype=self._dtype, device=dev)
+                             if self._engine.n_robots > 0 else None)
 
     # ------------------------------------------------------------------ physics step (:138-238)
     def _on_physics_step(self, delta_time: float):

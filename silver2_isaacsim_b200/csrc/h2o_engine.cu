@@ -75,6 +75,8 @@ struct h2o_engine {
     int32_t* am_slot_type = nullptr;
     int am_types = 0, am_slots = 0;
     const void* surface_eta = nullptr;  // (n,) per-body surface heights, borrowed, or nullptr = flat
+    long long* robot_offsets = nullptr;  // (n_robots_var + 1,) body offsets of unequal robots, or nullptr
+    long long n_robots_var = 0;
     int max_ctas_per_sm = 0;   // 0 = as many as fit
     int warp_compat = 0;       // components entry point reproduces the Warp twin's deviations
     int robot_cfg = -1;        // -1 = pick the CTA size by lane utilisation (tuning override: 0,1,2)
@@ -266,7 +268,7 @@ static int launch_direct(h2o_engine* e, const StepArgs& a, long long body_begin,
 template <typename S, int kLayout>
 static int launch_robot_wrench(h2o_engine* e, const StepArgs& a, long long robot_begin, cudaStream_t stream)
 {
-    const long long n_robots = a.n / a.bodies_per_robot;
+    const long long n_robots = a.robot_offsets ? a.n_robots_var : a.n / a.bodies_per_robot;
     const long long cnt = n_robots - robot_begin;
     if (cnt <= 0) return H2O_OK;
     const int grid = int((cnt * 32 + 255) / 256);
@@ -353,6 +355,10 @@ static int step_typed2(h2o_engine* e, StepArgs& a, cudaStream_t stream)
             if (rc) return rc;
         }
     }
+    if (a.out_wrench && a.robot_offsets) {  // unequal robots: every wrench from the written force / torque arrays
+        int rc = launch_robot_wrench<S, kLayout>(e, a, 0, stream);
+        if (rc) return rc;
+    }
     return H2O_OK;
 }
 
@@ -382,9 +388,11 @@ static int step_device(h2o_engine* e, int layout, const void* pos, const void* q
 {
     if (e->param_mode < 0) return fail(H2O_ERR_NOT_CONFIGURED, "no parameters set (h2o_set_params_*)");
     if (!(dt > 1e-6)) return H2O_OK;  // hydrodynamics_behavior.py:139
-    if (w && e->bodies_per_robot <= 0)
+    if (w && e->bodies_per_robot <= 0 && !e->robot_offsets)
         return fail(H2O_ERR_NOT_CONFIGURED, "robot wrench requested but h2o_set_articulation not called");
-    if (w && (n % e->bodies_per_robot) != 0)
+    if (w && e->robot_offsets && (n != e->n || first_body != 0))
+        return fail(H2O_ERR_NOT_CONFIGURED, "unequal robots (h2o_set_articulation_offsets) need whole-batch launches");
+    if (w && !e->robot_offsets && (n % e->bodies_per_robot) != 0)
         return fail(H2O_ERR_BAD_SHAPE, "n_bodies %lld is not a multiple of bodies_per_robot %d", n,
                     e->bodies_per_robot);
     StepArgs a;
@@ -404,6 +412,7 @@ static int step_device(h2o_engine* e, int layout, const void* pos, const void* q
     for (int k = 0; k < 3; ++k) a.current[k] = e->current[k];
     a.surface_z = e->surface_z;
     a.am_dense = e->am_dense; a.am_slot_type = e->am_slot_type; a.am_n_slots = e->am_slots;
+    a.robot_offsets = e->robot_offsets; a.n_robots_var = e->n_robots_var;
     a.surface_eta = e->surface_eta ? static_cast<const char*>(e->surface_eta) + size_t(first_body) * e->esz : nullptr;
     return e->dtype == H2O_F32 ? step_typed<float>(e, layout, a, stream) : step_typed<double>(e, layout, a, stream);
 }
@@ -496,6 +505,7 @@ int h2o_destroy(h2o_handle h)
     if (e->slot_type) cudaFree(e->slot_type);
     if (e->am_dense) cudaFree(e->am_dense);
     if (e->am_slot_type) cudaFree(e->am_slot_type);
+    if (e->robot_offsets) cudaFree(e->robot_offsets);
     if (e->prev) cudaFree(e->prev);
     if (e->stats) cudaFree(e->stats);
     e->magic = 0;
@@ -718,6 +728,33 @@ int h2o_set_articulation(h2o_handle h, int bodies_per_robot)
         return fail(H2O_ERR_BAD_SHAPE, "n_bodies %lld is not a multiple of bodies_per_robot %d", (long long)e->n,
                     bodies_per_robot);
     e->bodies_per_robot = bodies_per_robot;
+    if (e->robot_offsets) {  // equal runs replace an earlier h2o_set_articulation_offsets
+        DeviceGuard g(e->device);
+        cudaFree(e->robot_offsets);
+        e->robot_offsets = nullptr;
+        e->n_robots_var = 0;
+    }
+    return H2O_OK;
+}
+
+int h2o_set_articulation_offsets(h2o_handle h, int64_t n_robots, const int64_t* offsets_host)
+{
+    h2o_engine* e = check(h);
+    if (!e) return H2O_ERR_BAD_HANDLE;
+    if (n_robots < 1 || !offsets_host) return fail(H2O_ERR_BAD_ARGUMENT, "need n_robots >= 1 and offsets");
+    if (offsets_host[0] != 0 || offsets_host[n_robots] != e->n)
+        return fail(H2O_ERR_BAD_SHAPE, "offsets must start at 0 and end at n_bodies = %lld", (long long)e->n);
+    for (int64_t r = 0; r < n_robots; ++r)
+        if (offsets_host[r + 1] <= offsets_host[r])
+            return fail(H2O_ERR_BAD_ARGUMENT, "offsets must increase strictly (robot %lld is empty)", (long long)r);
+    DeviceGuard g(e->device);
+    if (e->robot_offsets) { cudaFree(e->robot_offsets); e->robot_offsets = nullptr; }
+    e->n_robots_var = 0;
+    std::vector<long long> tmp(offsets_host, offsets_host + n_robots + 1);
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&e->robot_offsets), tmp.size() * sizeof(long long)));
+    CUDA_TRY(cudaMemcpy(e->robot_offsets, tmp.data(), tmp.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    e->n_robots_var = n_robots;
+    e->bodies_per_robot = 0;
     return H2O_OK;
 }
 
@@ -1300,6 +1337,7 @@ static int dl_wrench(h2o_engine* e, const DLTensor* w, const void** out_ptr)
 {
     *out_ptr = nullptr;
     if (!w) return H2O_OK;
+    if (e->robot_offsets) return dl_check(e, w, "out_robot_wrench", e->n_robots_var, 6, false, out_ptr);
     if (e->bodies_per_robot <= 0)
         return fail(H2O_ERR_NOT_CONFIGURED, "robot wrench requested but h2o_set_articulation not called");
     return dl_check(e, w, "out_robot_wrench", e->n / e->bodies_per_robot, 6, false, out_ptr);

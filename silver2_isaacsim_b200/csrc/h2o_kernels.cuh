@@ -74,6 +74,10 @@ struct StepArgs {
     // optional non-flat water surface: (N,) surface height above surface_z at each body's
     // position, engine dtype, borrowed from the caller.  Direct kernel only.
     const void* surface_eta;
+    // optional articulation of UNEQUAL robots: robot r owns bodies [robot_offsets[r], robot_offsets[r+1]);
+    // nullptr = equal runs of bodies_per_robot.  Wrenches then come from robot_wrench_kernel.
+    const long long* robot_offsets;
+    long long n_robots_var;
 };
 
 // ---------------------------------------------------------------------------
@@ -699,16 +703,17 @@ __global__ void __launch_bounds__(256) robot_wrench_kernel(const __grid_constant
 {
     const long long robot = robot_begin + ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 32;
     const int lane = threadIdx.x & 31;
-    const long long n_robots = a.n / a.bodies_per_robot;
+    const long long n_robots = a.robot_offsets ? a.n_robots_var : a.n / a.bodies_per_robot;
     if (robot >= n_robots) return;
     constexpr int EP = (kLayout == LAYOUT_PHYSX) ? 7 : 3;
     const S* pos = reinterpret_cast<const S*>(a.pos);
     const S* Fp = reinterpret_cast<const S*>(a.out_force);
     const S* Tp = reinterpret_cast<const S*>(a.out_torque);
-    const long long b0 = robot * a.bodies_per_robot;
+    const long long b0 = a.robot_offsets ? a.robot_offsets[robot] : robot * a.bodies_per_robot;
+    const long long cnt = a.robot_offsets ? a.robot_offsets[robot + 1] - b0 : a.bodies_per_robot;
     const double bx = double(pos[EP * b0]), by = double(pos[EP * b0 + 1]), bz = double(pos[EP * b0 + 2]);
     double v[6] = {0, 0, 0, 0, 0, 0};
-    for (int j = lane; j < a.bodies_per_robot; j += 32) {
+    for (long long j = lane; j < cnt; j += 32) {
         const long long i = b0 + j;
         const double fx = double(Fp[3 * i]), fy = double(Fp[3 * i + 1]), fz = double(Fp[3 * i + 2]);
         const double ax = double(pos[EP * i]) - bx, ay = double(pos[EP * i + 1]) - by,

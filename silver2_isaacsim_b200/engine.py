@@ -216,6 +216,25 @@ class HydroEngine:
     def set_articulation(self, bodies_per_robot: int):
         L.check(self._lib.h2o_set_articulation(self._h, int(bodies_per_robot)))
         self.bodies_per_robot = int(bodies_per_robot)
+        self._n_robots_var = 0
+
+    def set_articulation_offsets(self, offsets):
+        """Robots of unequal size: robot ``r`` owns bodies ``[offsets[r], offsets[r+1])`` (``offsets[0] == 0``,
+        ``offsets[-1] == n_bodies``); the robot wrench output is then ``(len(offsets) - 1, 6)``."""
+        off = np.ascontiguousarray(np.asarray(offsets, dtype=np.int64))
+        if off.ndim != 1 or off.size < 2:
+            raise ValueError("offsets must be a 1-d array of n_robots + 1 entries")
+        L.check(self._lib.h2o_set_articulation_offsets(self._h, int(off.size - 1),
+                                                       off.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))))
+        self.bodies_per_robot = 0
+        self._n_robots_var = int(off.size - 1)
+
+    @property
+    def n_robots(self) -> int:
+        """Rows of the per-robot wrench output (0 without an articulation)."""
+        if getattr(self, "_n_robots_var", 0) > 0:
+            return self._n_robots_var
+        return self.n_bodies // self.bodies_per_robot if self.bodies_per_robot > 0 else 0
 
     def set_kernel(self, choice: str = "auto"):
         code = {"auto": L.H2O_KERNEL_AUTO, "tile": L.H2O_KERNEL_TILE, "direct": L.H2O_KERNEL_DIRECT}[choice]
@@ -269,9 +288,9 @@ class HydroEngine:
         if out_torque is None:
             out_torque = self._empty(self.n_bodies, 3)
         if want_wrench and out_robot_wrench is None:
-            if self.bodies_per_robot <= 0:
+            if self.n_robots <= 0:
                 raise ValueError("robot wrench requested but set_articulation() was not called")
-            out_robot_wrench = self._empty(self.n_bodies // self.bodies_per_robot, 6)
+            out_robot_wrench = self._empty(self.n_robots, 6)
         return out_force, out_torque, out_robot_wrench
 
     # ------------------------------------------------------------------ fused step

@@ -204,6 +204,44 @@ def test_params_struct_of_arrays(oracle, dev, dtype, src):
         e.set_params_soa(cols[:10])
 
 
+@pytest.mark.parametrize("kernel", ["tile", "direct"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["fp32", "fp64"])
+def test_unequal_robots_by_offsets(oracle, dev, dtype, kernel):
+    """Articulation given as offsets: robots of 19 links mixed with single-body buoys (the reference's
+    main scene is one SILVER2 + the Obsea buoy) and a few odd sizes; wrench about each robot's first body."""
+    rng = np.random.default_rng(3)
+    sizes = rng.choice([19, 1, 19, 1, 7, 40, 19], size=4000)
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    wl = W.heterogeneous_boxes(int(offsets[-1]), seed=71, xy_range=2.0)
+    e = _engine(wl, dtype, dev, kernel)
+    e.set_articulation_offsets(offsets)
+    assert e.n_robots == len(sizes)
+    F, T, Wr = _run_step(e, wl, dtype, dev, robot=True)
+    assert e.last_kernel == kernel and Wr.shape == (len(sizes), 6)
+    ref = _ref(oracle, wl)
+    if dtype == torch.float32:
+        scoring.assert_fp32(F, ref.force, "offset robots force", min_pass=0.9999)
+        scoring.assert_fp32(T, ref.torque, "offset robots torque", min_pass=0.9999)
+    else:
+        _check(wl, dtype, ref, F, T, "offset robots")
+    pos, Fr, Tr = wl.pos.astype(np.float64), ref.force, ref.torque
+    want = np.zeros((len(sizes), 6)); mag = np.zeros((len(sizes), 6))
+    for r in range(len(sizes)):
+        sl = slice(offsets[r], offsets[r + 1])
+        arm = pos[sl] - pos[offsets[r]]
+        want[r, :3] = Fr[sl].sum(0); want[r, 3:] = (Tr[sl] + np.cross(arm, Fr[sl])).sum(0)
+        mag[r, :3] = np.abs(Fr[sl]).sum(0); mag[r, 3:] = (np.abs(Tr[sl]) + np.abs(np.cross(arm, Fr[sl]))).sum(0)
+    err, _ = scoring.vec_err(Wr, want)
+    tol = (1e-5 if dtype == torch.float32 else 1e-11) * mag.max(axis=1) * 20
+    assert (err <= tol + 1e-6).all(), float((err / (tol + 1e-6)).max())
+    # equal runs again
+    e2 = _engine(wl, dtype, dev, kernel)
+    with pytest.raises(Exception):
+        e2.set_articulation_offsets([0, 5, 5, wl.n])      # empty robot
+    with pytest.raises(Exception):
+        e2.set_articulation_offsets([0, 5, wl.n - 1])     # does not end at n_bodies
+
+
 def test_step_sharded_robots_per_body_records(oracle, dev):
     """C4 shard: heterogeneous per-robot jitter (per-body records) + robot wrench, PhysX layout."""
     wl = W.sharded_robots(4099)

@@ -150,7 +150,7 @@ def test_batched_behavior_adapter(oracle, dev):
     masses = np.array([cfg["masses"].get(P.match_part(nm, cfg) or "", 512.5) for nm in names], dtype=np.float32)
     tt = lambda a: torch.as_tensor(a, device=dev)
     view = FakeRigidPrimView(tt(pos), tt(q[:, [3, 0, 1, 2]].copy()), tt(vel), tt(masses))
-    b = BatchedHydrodynamicsBehavior(names, view, device="cuda:0")
+    b = BatchedHydrodynamicsBehavior(names, view, device="cuda:0", robot_offsets=[0, 19, 20])  # robot + buoy
     assert b.part_of[0] == "body" and b.part_of[1] == "coxa" and b.part_of[-1] is None
     assert b.exposed["Obsea_Buoy"].xDimension == 1.0 and b.exposed["Tibia_5"].linearDamping == 20.0
     b._on_physics_step(1 / 60)          # not playing yet: nothing happens (engine is None)
@@ -168,6 +168,13 @@ def test_batched_behavior_adapter(oracle, dev):
         scoring.assert_fp32(F.cpu().numpy(), ref.force, "behaviour force", min_pass=1.0)
         scoring.assert_fp32(T.cpu().numpy(), ref.torque, "behaviour torque", min_pass=1.0)
         assert torch.equal(Ppos, view.pos)
+        # per-robot net wrench: the 19-link robot about its Body prim, the buoy about itself
+        wr = b.robot_wrench.double().cpu().numpy()
+        assert wr.shape == (2, 6)
+        want = oracle.robot_wrench(pos[:19], ref.force[:19], ref.torque[:19], 19)[0]
+        assert np.abs(wr[0] - want).max() <= 2e-4 * (np.abs(ref.force[:19]).sum() + np.abs(ref.torque[:19]).sum())
+        assert np.allclose(wr[1, :3], ref.force[19], rtol=2e-5, atol=1e-5)
+        assert np.allclose(wr[1, 3:], ref.torque[19], rtol=2e-5, atol=1e-5)
     view.valid = False
     view.applied = None
     b._on_physics_step(dt)              # invalid view: skipped (:139)
