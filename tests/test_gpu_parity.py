@@ -242,6 +242,64 @@ def test_unequal_robots_by_offsets(oracle, dev, dtype, kernel):
         e2.set_articulation_offsets([0, 5, wl.n - 1])     # does not end at n_bodies
 
 
+def test_random_configurations(oracle, dev):
+    """Seeded sweep over the configuration space: batch sizes around every granule (1 body ... a few
+    tiles), ingest layout, parameter mode, kernel request, quaternion order, robot size, precision."""
+    from silver2_isaacsim_b200 import HydroEngine, params as P
+
+    rng = np.random.default_rng(2026)
+    sizes = [1, 2, 3, 4, 5, 31, 32, 33, 127, 128, 129, 255, 257, 1000, 4097, 37_887, 37_888, 37_889, 75_777, 131_073]
+    for case in range(72):
+        bpr = int(rng.choice([0, 0, 1, 3, 19, 20]))
+        n = int(rng.choice(sizes))
+        if bpr:
+            n = max(bpr, n // bpr * bpr)
+        dtype = torch.float32 if rng.random() < 0.6 else torch.float64
+        layout = str(rng.choice(["split", "physx", "view"]))
+        kernel = str(rng.choice(["auto", "tile", "direct"]))
+        order = str(rng.choice(["xyzw", "wxyz"]))
+        table = rng.random() < 0.4
+        wl = W.heterogeneous_boxes(n, seed=3000 + case, xy_range=3.0,
+                                   dtype=np.float32 if dtype == torch.float32 else np.float64)
+        coeff = np.asarray(wl.coeff, dtype=np.float64)
+        e = HydroEngine(n, dtype=dtype, device=dev, quat_order=order)
+        e.set_globals(wl.rho, wl.g)
+        if table:
+            n_types, n_slots = int(rng.integers(1, 6)), int(rng.integers(1, 24))
+            tab = coeff[rng.choice(n, n_types)]
+            slots = rng.integers(0, n_types, n_slots).astype(np.int32)
+            coeff = tab[slots[np.arange(n) % n_slots]]
+            e.set_part_table(tab, slots)
+        else:
+            e.set_params_per_body(coeff)
+        e.set_articulation(bpr)
+        e.set_kernel(kernel)
+        what = f"case {case}: n={n} bpr={bpr} {dtype} {layout} {kernel} {order} table={table}"
+        quat = wl.quat_xyzw if order == "xyzw" else wl.quat_xyzw[:, [3, 0, 1, 2]]
+        wl_in = W.Workload(**{**wl.__dict__, "quat_xyzw": np.ascontiguousarray(quat)})   # what the caller hands over
+        out = _run_step(e, wl_in, dtype, dev, layout, robot=bpr > 0)
+        F, T = out[0], out[1]
+        ref = oracle.step(P.coeff_to_ctor_rows(coeff, wl.rho, wl.g), coeff[:, 10].copy(), wl.pos, wl.quat_xyzw,
+                          wl.lin_vel, wl.ang_vel, wl.prev_lin, wl.prev_ang, wl.dt)
+        if dtype == torch.float32:
+            assert scoring.fp32_ok(F, ref.force).mean() >= 0.9995, what
+            assert scoring.fp32_ok(T, ref.torque).mean() >= 0.9995, what
+            assert scoring.fp32_ok(F, ref.force, rel=1e-4).all() and scoring.fp32_ok(T, ref.torque, rel=1e-4).all(), what
+        else:
+            scale = scoring.force_scale(coeff, wl.rho, wl.g)
+            pn = np.abs(wl.pos).max(axis=1).astype(float) * np.abs(ref.force).max(axis=1)
+            assert scoring.fp64_ok(F, ref.force, scale).all() and scoring.fp64_ok(T, ref.torque, scale, extra=pn).all(), what
+        if bpr:
+            want = oracle.robot_wrench(wl.pos, ref.force, ref.torque, bpr)
+            mag = oracle.robot_wrench(wl.pos, np.abs(ref.force), np.abs(ref.torque), bpr)
+            err, _ = scoring.vec_err(out[2], want)
+            tol = (1e-5 if dtype == torch.float32 else 1e-11) * np.abs(mag).max(axis=1) * 20
+            assert (err <= tol + 1e-6).all(), what
+        prev = e.prev_velocities().double().cpu().numpy()
+        assert (prev[:, :3] == wl.lin_vel.astype(np.float64)).all() and (prev[:, 3:] == wl.ang_vel.astype(np.float64)).all(), what
+        e.close()
+
+
 def test_step_sharded_robots_per_body_records(oracle, dev):
     """C4 shard: heterogeneous per-robot jitter (per-body records) + robot wrench, PhysX layout."""
     wl = W.sharded_robots(4099)
