@@ -300,6 +300,29 @@ def test_random_configurations(oracle, dev):
         e.close()
 
 
+@pytest.mark.parametrize("kernel", ["tile", "direct"])
+def test_carried_velocities_over_several_steps(oracle, dev, kernel):
+    """The engine-owned v_prev / w_prev (hydrodynamics_behavior.py:196-202, :237-238) across steps with
+    changing velocities and step sizes, a skipped step (dt <= 1e-6 leaves the state alone) included."""
+    wl = W.sharded_robots(3000)
+    e = _engine(wl, torch.float32, dev, kernel)
+    rng = np.random.default_rng(5)
+    prev_l, prev_a = np.zeros_like(wl.lin_vel, dtype=np.float64), np.zeros_like(wl.ang_vel, dtype=np.float64)
+    pos, quat = _t(wl.pos, torch.float32, dev), _t(wl.quat_xyzw, torch.float32, dev)
+    v, w = wl.lin_vel.copy(), wl.ang_vel.copy()
+    for k, dt in enumerate([1 / 120, 1 / 60, 1e-7, 1 / 240, 1 / 120]):
+        F, T, Wr = e.step(pos, quat, _t(v, torch.float32, dev), _t(w, torch.float32, dev), dt, robot_wrench=True)
+        if dt > 1e-6:
+            ref = oracle.step(wl.ctor_rows(), wl.masses(), wl.pos, wl.quat_xyzw, v, w, prev_l, prev_a, dt)
+            prev_l, prev_a = ref.prev_lin, ref.prev_ang
+            scoring.assert_fp32(F.cpu().numpy(), ref.force, f"step {k} force", min_pass=0.9999)
+            scoring.assert_fp32(T.cpu().numpy(), ref.torque, f"step {k} torque", min_pass=0.9999)
+        got = e.prev_velocities().double().cpu().numpy()
+        assert (got[:, :3] == prev_l).all() and (got[:, 3:] == prev_a).all(), k
+        v = (v + rng.normal(size=v.shape).astype(np.float32) * 0.05).astype(np.float32)
+        w = (w + rng.normal(size=w.shape).astype(np.float32) * 0.05).astype(np.float32)
+
+
 def test_step_sharded_robots_per_body_records(oracle, dev):
     """C4 shard: heterogeneous per-robot jitter (per-body records) + robot wrench, PhysX layout."""
     wl = W.sharded_robots(4099)
