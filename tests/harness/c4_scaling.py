@@ -6,12 +6,12 @@ The fleet is generated in 8 blocks of 110 592 robots (seed = SEED_BASE + 40 + bl
 set is the same for every world size; rank r owns blocks [r*8/G, (r+1)*8/G).  Each rank also scores a
 2^16-robot sample of its shard against the float64 oracle (fp32 criteria of tests/scoring.py).
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 tools/c4_scaling.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 tests/harness/c4_scaling.py
 Prints one JSON line on rank 0.
 """
 import json, os, sys
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from silver2_isaacsim_b200 import HydroEngine, sharding, workloads as W
 

@@ -8,7 +8,7 @@ unmodified reference raises (wet, at rest).  Writes a markdown table to stdout.
 """
 import os, sys
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import hydro_oracle as O
 from silver2_isaacsim_b200 import HydroEngine, workloads as W
 

@@ -1,6 +1,6 @@
 """Precision study on the CPU: the model header (host-instantiated, tests/host_emul) vs the f64 oracle.
 
-    python tools/precision_study.py [n_bodies]
+    python tests/harness/precision_study.py [n_bodies]
 
 Prints, per workload and precision policy, how many force / torque vectors miss the fp32
 criterion of SURVEY.md 8(d) and the error quantiles.  This is how the mixed-precision policy of
@@ -11,7 +11,7 @@ import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import hydro_oracle as O  # noqa: E402
 from silver2_isaacsim_b200 import workloads as W  # noqa: E402
 from tests import emul, scoring  # noqa: E402

@@ -4,7 +4,7 @@ travel to the GPU box, which is why bench.py's CPU arm is the C port).  Prints b
 (b) the C oracle port on the same inputs, for scale."""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import ref_numba, hydro_oracle as O
 from silver2_isaacsim_b200 import workloads as W
 

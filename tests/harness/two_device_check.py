@@ -2,7 +2,7 @@
 (every entry point must switch to its handle's device and back)."""
 import os, sys
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from silver2_isaacsim_b200 import HydroEngine, workloads as W
 from oracle import hydro_oracle as O
 from tests import scoring

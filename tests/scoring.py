@@ -37,7 +37,7 @@ def assert_fp32(x, y, what, min_pass=0.99999, hard_factor=10.0):
     """Strict criterion for >= min_pass of the vectors; none beyond hard_factor x the tolerance.
 
     The residual (~1e-6 of random bodies) are torques whose large terms cancel by chance;
-    fp32 storage cannot resolve them (measured in tools/precision_study.py).
+    fp32 storage cannot resolve them (measured in tests/harness/precision_study.py).
     """
     err, den = vec_err(x, y)
     tol = np.maximum(FP32_REL * den, FP32_ABS)
