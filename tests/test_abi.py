@@ -56,12 +56,12 @@ def test_create_fails_loudly_without_gpu(built_lib):
 
 def test_product_never_imports_the_oracle():
     """Only tests/, __graft_entry__.smoke() and bench.py may touch oracle/."""
-    pkg = os.path.join(ROOT, "silver2_isaacsim_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
-                text = open(os.path.join(dirpath, f)).read()
-                assert "hydro_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
+    for top in ("silver2_isaacsim_b200", "tools", "examples", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".c")):
+                    text = open(os.path.join(dirpath, f)).read()
+                    assert "hydro_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
 
 
 def test_headers_are_plain_c_and_link(built_lib, tmp_path):
