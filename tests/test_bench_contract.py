@@ -40,3 +40,16 @@ def test_b200_arm_fails_loudly_without_gpu():
                          capture_output=True, text=True, timeout=300)
     assert res.returncode != 0 and "no CPU path" in (res.stderr + res.stdout)
     assert res.stdout.strip() == ""  # no fabricated line
+
+
+def test_tools_and_harnesses_compile():
+    """Every stand-alone script (tools/, tests/harness/, examples/) at least byte-compiles."""
+    import glob
+    import py_compile
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    scripts = [p for d in ("tools", os.path.join("tests", "harness"), "examples")
+               for p in glob.glob(os.path.join(root, d, "*.py"))]
+    assert len(scripts) >= 15
+    for p in scripts:
+        py_compile.compile(p, doraise=True, cfile=os.path.join("/tmp", "h2o_pyc_" + os.path.basename(p) + "c"))
