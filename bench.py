@@ -508,7 +508,10 @@ def run_b200(args):
             extra = {"error": repr(exc)}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(args.cpu_sample)
+        try:
+            cpu = cpu_baseline(args.cpu_sample)
+        except Exception as exc:  # the CPU leg must never lose the headline line
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed", "error": repr(exc)}
 
     if rank == 0:
         line = {
