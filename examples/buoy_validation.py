@@ -37,12 +37,9 @@ F, T = eng.bind(pos, quat, v, w)
 eng.set_rollout_mode(free_bodies=True, gravity=wl.g)   # every captured step: forces, then the stepper
 
 GRAPH = 100
-eng.capture_rollout(GRAPH - 1, wl.dt)                  # capture runs one eager step first
+eng.capture_rollout(GRAPH, wl.dt)
 trace, rtf = VelocityTrace(args.csv), RtfMeter(report_every=1000)
 for k in range(args.steps // GRAPH):
-    if k:
-        eng.step_bound(wl.dt)
-        eng.integrate_free_bodies(pos, quat, v, w, F, T, wl.dt, wl.g)
     eng.launch_rollout()
     torch.cuda.synchronize()
     rtf.on_physics_step(wl.dt, GRAPH)

@@ -87,7 +87,7 @@ H2O_API int h2o_set_globals(h2o_handle h, double water_density, double gravity);
  * by the caller); the model then sees p_z - surface_z - eta[i] where the reference uses p_z
  * (analyze_submersion_and_cob, numba_hydrodynamics.py:59-105, tests keypoints against z = 0).  The
  * pointer is borrowed and read by every later step until replaced (update the array in place between
- * steps; a rollout captured with h2o_capture_rollout keeps the pointer it was captured with); NULL =
+ * steps; replacing the pointer drops a rollout captured with h2o_capture_rollout); NULL =
  * flat.  Steps with a height field run on the per-body kernel. */
 H2O_API int h2o_set_surface_heights(h2o_handle h, const void* eta_dev);
 
@@ -196,7 +196,10 @@ H2O_API int h2o_step_bound(h2o_handle h, double dt, h2o_stream stream);
 
 /* CUDA-graph rollout over the bound tensors: n_steps back-to-back steps captured once,
  * replayed with one launch (the reference captures a single dim=1 kernel,
- * warp_hydrodynamics_wrapper.py:101-120). */
+ * warp_hydrodynamics_wrapper.py:101-120).  Capturing launches nothing: the carried velocities and
+ * (free-body mode) the bound state are exactly as before the call.  The graph bakes in the engine's
+ * device buffers and constants, so every h2o_set_* / h2o_enable_stats / h2o_bind / h2o_unbind call drops
+ * it: h2o_launch_rollout then returns H2O_ERR_NOT_CONFIGURED until the rollout is captured again. */
 H2O_API int h2o_capture_rollout(h2o_handle h, int n_steps, double dt, h2o_stream stream);
 /* Rollout mode: 0 = static state (force-only rollout), 1 = free bodies: after each step the bound
  * pose / velocity tensors are integrated in place by h2o_integrate_free_bodies (split layout). */

@@ -16,6 +16,15 @@ life cycle and parameter surface --
 against the three ``RigidPrimView`` methods the reference uses (``get_world_poses``,
 ``get_velocities``, ``apply_forces_and_torques_at_pos`` + ``get_masses`` / ``is_valid``), so it
 runs unchanged inside Isaac Sim and, in tests, against a stand-in view.
+
+Deliberate deviation: the reference script evaluates forces through its Warp wrapper
+(hydrodynamics_behavior.py:19, :155), whose kernel rotates the accelerations FORWARD into the
+"body" frame (warp_hydrodynamics.py:216-217) where the Numba path uses R^T
+(numba_hydrodynamics.py:229-230), so its linear added-mass force is -m R^2 a instead of -m a.
+BASELINE.json's north star pins this engine to the NUMBA semantics, and the fused step implements
+only those; for rotated bodies with a non-zero added-mass coefficient (Body: 0.2 / 0.1) the forces
+therefore differ from the Warp production path by that term.  The Warp
+deviations are available for A/B through ``HydroEngine.components`` with ``set_warp_compat(True)``.
 """
 from __future__ import annotations
 

@@ -99,7 +99,20 @@ struct h2o_engine {
     void* hp_pin[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaStream_t hp_stream[HOST_PIPE_STREAMS] = {nullptr, nullptr, nullptr};
     cudaStream_t capture_stream = nullptr;  // graph capture never runs on the caller's (maybe legacy) stream
+    bool dry_run = false;  // launch helpers do their one-time attribute / occupancy set-up and count, but launch nothing
 };
+
+// A captured rollout bakes in device pointers (coefficients, slot maps, dense added mass, robot offsets)
+// and constants (rho, g, environment, quaternion order, statistics flag, kernel / tile choice).  Every
+// setter that changes one of them drops the graph; h2o_launch_rollout then reports NOT_CONFIGURED until
+// h2o_capture_rollout is called again, instead of replaying kernels over freed or stale memory.
+static void invalidate_graph(h2o_engine* e)
+{
+    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+    if (e->graph) { cudaGraphDestroy(e->graph); e->graph = nullptr; }
+    e->graph_steps = 0;
+    e->graph_launches_per_replay = 0;
+}
 
 static h2o_engine* check(h2o_handle h)
 {
@@ -207,6 +220,9 @@ static int launch_tile(h2o_engine* e, StepArgs& a, cudaStream_t stream)
         ctas_per_sm[dev] = c;
     }
     const int tb_max = tile_bodies_for(C::kThreads, sizeof(S), kRobot ? a.bodies_per_robot : 0);
+    if (tb_max <= 0)
+        return fail(H2O_ERR_BAD_ARGUMENT, "a robot of %d bodies does not fit a %d-thread tile (H2O_ROBOT_CFG?)",
+                    a.bodies_per_robot, C::kThreads);
     if (C::kBpr > 0 && (a.bodies_per_robot != C::kBpr ||
                         tb_max != tile_bodies_static(C::kThreads, int(sizeof(S)), C::kBpr > 0 ? C::kBpr : 1)))
         return fail(H2O_ERR_BAD_ARGUMENT, "kernel specialised for %d-body robots launched with %d", C::kBpr,
@@ -217,6 +233,11 @@ static int launch_tile(h2o_engine* e, StepArgs& a, cudaStream_t stream)
     a.tile_bodies = tb_max;
     a.n_tiles = int(std::min<long long>(a.n / tb_max, 0x7fffffff));
     const int grid = int(std::max<long long>(1, std::min<long long>(a.n_tiles, slots)));
+    if (e->dry_run) {
+        e->launches += 1;
+        e->last_ctas_per_sm = cps;
+        return H2O_OK;
+    }
     if (e->use_pdl) {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof cfg);
@@ -245,6 +266,10 @@ static int launch_direct(h2o_engine* e, const StepArgs& a, long long body_begin,
     const long long cnt = a.n - body_begin;
     if (cnt <= 0) return H2O_OK;
     const int grid = int((cnt + 255) / 256);
+    if (e->dry_run) {
+        e->launches += 1;
+        return H2O_OK;
+    }
     if (e->use_pdl) {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof cfg);
@@ -272,6 +297,10 @@ static int launch_robot_wrench(h2o_engine* e, const StepArgs& a, long long robot
     const long long cnt = n_robots - robot_begin;
     if (cnt <= 0) return H2O_OK;
     const int grid = int((cnt * 32 + 255) / 256);
+    if (e->dry_run) {
+        e->launches += 1;
+        return H2O_OK;
+    }
     robot_wrench_kernel<S, kLayout><<<grid, 256, 0, stream>>>(a, robot_begin);
     CUDA_TRY(cudaGetLastError());
     e->launches += 1;
@@ -285,6 +314,8 @@ static int step_typed2(h2o_engine* e, StepArgs& a, cudaStream_t stream)
     const bool robots = a.bodies_per_robot > 0 && a.out_wrench != nullptr;
     const int TB = robots ? tile_bodies_for(RobotCfgs<S>::C::kThreads, sizeof(S), a.bodies_per_robot)
                           : tile_bodies_for(DC::kThreads, sizeof(S), 0);
+    // defensive only: every public entry point already rejects tensors that are not 16-byte aligned
+    // (check_ptrs / dl_check), so this guards internal callers that slice buffers (h2o_step_host)
     bool ptr_ok = aligned16(a.pos) && aligned16(a.lin) && aligned16(a.prev) && aligned16(a.out_force) &&
                   aligned16(a.out_torque) && (kLayout == LAYOUT_PHYSX || aligned16(a.quat)) &&
                   (kLayout != LAYOUT_SPLIT || aligned16(a.ang)) &&
@@ -517,6 +548,7 @@ int h2o_set_globals(h2o_handle h, double water_density, double gravity)
 {
     h2o_engine* e = check(h);
     if (!e) return H2O_ERR_BAD_HANDLE;
+    { DeviceGuard gi(e->device); invalidate_graph(e); }
     e->rho = water_density;
     e->grav = gravity;
     return H2O_OK;
@@ -526,6 +558,7 @@ int h2o_set_environment(h2o_handle h, const double current_xyz[3], double surfac
 {
     h2o_engine* e = check(h);
     if (!e) return H2O_ERR_BAD_HANDLE;
+    { DeviceGuard gi(e->device); invalidate_graph(e); }
     for (int k = 0; k < 3; ++k) e->current[k] = current_xyz ? current_xyz[k] : 0.0;
     e->surface_z = surface_z;
     return H2O_OK;
@@ -535,6 +568,7 @@ int h2o_set_surface_heights(h2o_handle h, const void* eta_dev)
 {
     h2o_engine* e = check(h);
     if (!e) return H2O_ERR_BAD_HANDLE;
+    { DeviceGuard gi(e->device); invalidate_graph(e); }
     e->surface_eta = eta_dev;
     return H2O_OK;
 }
@@ -544,6 +578,7 @@ int h2o_set_part_table(h2o_handle h, int n_types, const double* table_host, int 
 {
     h2o_engine* e = check(h);
     if (!e) return H2O_ERR_BAD_HANDLE;
+    { DeviceGuard gi(e->device); invalidate_graph(e); }
     if (n_types < 1 || n_types > MAX_TABLE_TYPES)
         return fail(H2O_ERR_BAD_ARGUMENT, "n_types %d out of range [1,%d]", n_types, MAX_TABLE_TYPES);
     if (n_slots < 1 || n_slots > MAX_TABLE_SLOTS)
@@ -579,6 +614,7 @@ int h2o_set_added_mass_dense(h2o_handle h, int n_types, const double* matrices_h
 {
     h2o_engine* e = check(h);
     if (!e) return H2O_ERR_BAD_HANDLE;
+    { DeviceGuard gi(e->device); invalidate_graph(e); }
     DeviceGuard g(e->device);
     if (n_types == 0) {  // back to the wrapper's diagonal
         if (e->am_dense) { cudaFree(e->am_dense); e->am_dense = nullptr; }
@@ -636,6 +672,7 @@ int h2o_set_params_per_body(h2o_handle h, const void* coeff, int src_dtype, h2o_
 {
     h2o_engine* e = check(h);
     if (!e) return H2O_ERR_BAD_HANDLE;
+    { DeviceGuard gi(e->device); invalidate_graph(e); }
     if (!coeff) return fail(H2O_ERR_BAD_ARGUMENT, "coeff is NULL");
     if (src_dtype != H2O_F32 && src_dtype != H2O_F64) return fail(H2O_ERR_BAD_DTYPE, "bad src_dtype");
     DeviceGuard g(e->device);
@@ -679,6 +716,7 @@ int h2o_set_params_soa(h2o_handle h, const void* const cols[11], int src_dtype, 
 {
     h2o_engine* e = check(h);
     if (!e) return H2O_ERR_BAD_HANDLE;
+    { DeviceGuard gi(e->device); invalidate_graph(e); }
     if (!cols) return fail(H2O_ERR_BAD_ARGUMENT, "cols is NULL");
     if (src_dtype != H2O_F32 && src_dtype != H2O_F64) return fail(H2O_ERR_BAD_DTYPE, "bad src_dtype");
     DeviceGuard g(e->device);
@@ -723,6 +761,7 @@ int h2o_set_articulation(h2o_handle h, int bodies_per_robot)
 {
     h2o_engine* e = check(h);
     if (!e) return H2O_ERR_BAD_HANDLE;
+    { DeviceGuard gi(e->device); invalidate_graph(e); }
     if (bodies_per_robot < 0) return fail(H2O_ERR_BAD_ARGUMENT, "bodies_per_robot must be >= 0");
     if (bodies_per_robot > 0 && e->n % bodies_per_robot != 0)
         return fail(H2O_ERR_BAD_SHAPE, "n_bodies %lld is not a multiple of bodies_per_robot %d", (long long)e->n,
@@ -741,6 +780,7 @@ int h2o_set_articulation_offsets(h2o_handle h, int64_t n_robots, const int64_t* 
 {
     h2o_engine* e = check(h);
     if (!e) return H2O_ERR_BAD_HANDLE;
+    { DeviceGuard gi(e->device); invalidate_graph(e); }
     if (n_robots < 1 || !offsets_host) return fail(H2O_ERR_BAD_ARGUMENT, "need n_robots >= 1 and offsets");
     if (offsets_host[0] != 0 || offsets_host[n_robots] != e->n)
         return fail(H2O_ERR_BAD_SHAPE, "offsets must start at 0 and end at n_bodies = %lld", (long long)e->n);
@@ -762,6 +802,7 @@ int h2o_set_quat_order(h2o_handle h, int order)
 {
     h2o_engine* e = check(h);
     if (!e) return H2O_ERR_BAD_HANDLE;
+    { DeviceGuard gi(e->device); invalidate_graph(e); }
     if (order != H2O_QUAT_XYZW && order != H2O_QUAT_WXYZ) return fail(H2O_ERR_BAD_ARGUMENT, "bad quaternion order");
     e->quat_order = order;
     return H2O_OK;
@@ -771,6 +812,7 @@ int h2o_set_kernel(h2o_handle h, int choice)
 {
     h2o_engine* e = check(h);
     if (!e) return H2O_ERR_BAD_HANDLE;
+    { DeviceGuard gi(e->device); invalidate_graph(e); }
     if (choice < H2O_KERNEL_AUTO || choice > H2O_KERNEL_DIRECT) return fail(H2O_ERR_BAD_ARGUMENT, "bad kernel choice");
     e->kernel_choice = choice;
     return H2O_OK;
@@ -788,6 +830,7 @@ int h2o_set_tile_config(h2o_handle h, int cfg)
 {
     h2o_engine* e = check(h);
     if (!e) return H2O_ERR_BAD_HANDLE;
+    { DeviceGuard gi(e->device); invalidate_graph(e); }
     if (cfg < 0 || cfg > 11) return fail(H2O_ERR_BAD_ARGUMENT, "tile config must be in [0,11]");
     e->tile_cfg = cfg;
     return H2O_OK;
@@ -797,6 +840,7 @@ int h2o_enable_stats(h2o_handle h, int enable)
 {
     h2o_engine* e = check(h);
     if (!e) return H2O_ERR_BAD_HANDLE;
+    { DeviceGuard gi(e->device); invalidate_graph(e); }
     e->stats_on = enable != 0;
     return H2O_OK;
 }
@@ -930,8 +974,7 @@ int h2o_bind(h2o_handle h, int layout, const void* pos, const void* quat, const 
     e->b_pos = pos; e->b_quat = quat; e->b_lin = lin_vel; e->b_ang = ang_vel;
     e->b_f = out_force; e->b_t = out_torque; e->b_w = out_robot_wrench;
     e->bound = true;
-    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
-    if (e->graph) { cudaGraphDestroy(e->graph); e->graph = nullptr; }
+    invalidate_graph(e);
     return H2O_OK;
 }
 
@@ -941,8 +984,7 @@ int h2o_unbind(h2o_handle h)
     if (!e) return H2O_ERR_BAD_HANDLE;
     e->bound = false;
     DeviceGuard g(e->device);
-    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
-    if (e->graph) { cudaGraphDestroy(e->graph); e->graph = nullptr; }
+    invalidate_graph(e);
     return H2O_OK;
 }
 
@@ -968,6 +1010,10 @@ static int integrate_device(h2o_engine* e, void* pos, void* quat, void* lin, voi
     a.quat_wxyz = e->quat_order == H2O_QUAT_WXYZ;
     a.dt = dt; a.gravity = gravity;
     const int grid = int((e->n + 255) / 256);
+    if (e->dry_run) {
+        e->launches += 1;
+        return H2O_OK;
+    }
     if (e->dtype == H2O_F32) free_body_kernel<float><<<grid, 256, 0, s>>>(a);
     else free_body_kernel<double><<<grid, 256, 0, s>>>(a);
     CUDA_TRY(cudaGetLastError());
@@ -991,6 +1037,7 @@ int h2o_set_rollout_mode(h2o_handle h, int free_bodies, double gravity)
 {
     h2o_engine* e = check(h);
     if (!e) return H2O_ERR_BAD_HANDLE;
+    { DeviceGuard gi(e->device); invalidate_graph(e); }
     e->rollout_free_bodies = free_bodies != 0;
     e->rollout_gravity = gravity;
     return H2O_OK;
@@ -1016,23 +1063,26 @@ int h2o_capture_rollout(h2o_handle h, int n_steps, double dt, h2o_stream stream)
     if (n_steps < 1) return fail(H2O_ERR_BAD_ARGUMENT, "n_steps must be >= 1");
     DeviceGuard g(e->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
-    if (e->graph) { cudaGraphDestroy(e->graph); e->graph = nullptr; }
-    // One eager step first (on the caller's stream) so that every per-kernel attribute / occupancy
-    // query happens outside capture.  The capture itself runs on an engine-owned stream: the
-    // caller's stream may be the legacy default stream, which cannot be captured.
+    invalidate_graph(e);
+    // One DRY step first: every per-kernel attribute / occupancy query happens outside capture and the
+    // launches of one step are counted, but nothing is launched, so capturing does not advance the
+    // carried velocities or (free-body mode) the bound state.  The capture itself runs on an
+    // engine-owned stream: the caller's stream may be the legacy default stream, which cannot be captured.
     const int64_t before0 = e->launches;
+    e->dry_run = true;
     int rc = rollout_step(e, dt, s);
-    if (rc) return rc;
-    CUDA_TRY(cudaStreamSynchronize(s));
+    e->dry_run = false;
     const int64_t per_step = e->launches - before0;
+    e->launches = before0;
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s));  // order the capture stream after the caller's queued work
     if (!e->capture_stream) CUDA_TRY(cudaStreamCreateWithFlags(&e->capture_stream, cudaStreamNonBlocking));
     s = e->capture_stream;
     CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
     for (int i = 0; i < n_steps && rc == H2O_OK; ++i) rc = rollout_step(e, dt, s);
     cudaGraph_t graph = nullptr;
     cudaError_t err = cudaStreamEndCapture(s, &graph);
-    e->launches = before0 + per_step;  // captured launches did not execute
+    e->launches = before0;  // captured launches did not execute
     if (rc) {
         if (graph) cudaGraphDestroy(graph);
         return rc;

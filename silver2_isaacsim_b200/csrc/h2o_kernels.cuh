@@ -18,7 +18,7 @@
 //                      no uncoalesced or partial-sector traffic.  Optional
 //                      per-robot wrench summed out of shared memory.
 //   step_direct_kernel one thread per body, plain global loads; used for small
-//                      batches (latency-bound), unaligned pointers and tile tails.
+//                      batches (latency-bound), tile tails and the f4 generalisations.
 //   components_kernel  batched solve_hydrodynamics in the reference's full signature
 //                      (eight vectors + sub_ratio), optional Warp-twin compatibility.
 //   robot_wrench_kernel  one warp per robot, shuffle reduction (tails, big robots).

@@ -366,7 +366,9 @@ class HydroEngine:
             force.data_ptr(), torque.data_ptr(), float(dt), float(gravity), _stream_ptr(self.device)))
 
     def capture_rollout(self, n_steps: int, dt: float):
-        """Capture ``n_steps`` back-to-back steps over the bound tensors into one CUDA graph."""
+        """Capture ``n_steps`` back-to-back steps over the bound tensors into one CUDA graph.  Nothing is
+        launched while capturing (state and carried velocities stay as they are); any later ``set_*`` /
+        ``enable_stats`` / ``bind`` call drops the graph and ``launch_rollout`` raises until re-captured."""
         L.check(self._lib.h2o_capture_rollout(self._h, int(n_steps), float(dt), _stream_ptr(self.device)))
 
     def launch_rollout(self):

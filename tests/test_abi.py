@@ -16,13 +16,23 @@ def _declared_symbols():
     return sorted(set(names))
 
 
-def test_library_exports_every_declared_symbol(built_lib):
+def _check_exports(built_lib):
     declared = _declared_symbols()
     assert len(declared) >= 38
     for name in declared:
         assert hasattr(built_lib, name), f"{name} declared in include/*.h but not exported"
     from silver2_isaacsim_b200 import _lib
     assert sorted(_lib.SIGNATURES) == declared  # the ctypes table binds exactly the declared ABI
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    _check_exports(built_lib)
+
+
+@pytest.mark.gpu
+def test_library_exports_every_declared_symbol_on_the_gpu_box(built_lib):
+    """Same check, run by the driver's `-m gpu` pass on the B200 box (the shipped .so, not a rebuild)."""
+    _check_exports(built_lib)
 
 
 def test_no_torch_or_cxx_types_in_the_abi():
@@ -64,8 +74,7 @@ def test_product_never_imports_the_oracle():
                     assert "hydro_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
 
 
-def test_headers_are_plain_c_and_link(built_lib, tmp_path):
-    """include/*.h compile as C99 and the example C host links against the library."""
+def _check_c_host(built_lib, tmp_path):
     import subprocess
     from silver2_isaacsim_b200 import _lib
     inc = os.path.join(ROOT, "include")
@@ -87,3 +96,17 @@ def test_headers_are_plain_c_and_link(built_lib, tmp_path):
         assert abs(val - 7038.675) < 0.01
     else:
         assert res.returncode == 1 and "no CPU path" in res.stderr  # fails loudly without a GPU
+
+
+def test_headers_are_plain_c_and_link(built_lib, tmp_path):
+    """include/*.h compile as C99 and the example C host links against the library."""
+    _check_c_host(built_lib, tmp_path)
+
+
+@pytest.mark.gpu
+def test_c_host_runs_on_the_gpu_box(built_lib, tmp_path):
+    """The plain-C host (examples/c_host.c) drives the engine on the B200 and gets GV1's buoyancy."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    _check_c_host(built_lib, tmp_path)

@@ -455,13 +455,71 @@ def test_bound_step_and_graph_rollout_equal_eager(dev):
                 for _ in range(4):
                     e.step_bound(wl.dt)
             else:
-                e.capture_rollout(3, wl.dt)  # capture runs one eager step first
+                e.capture_rollout(4, wl.dt)  # capturing launches nothing and leaves the state alone
+                assert e.launch_count == 0
                 e.launch_rollout()
         torch.cuda.synchronize()
         outs.append((F.clone(), T.clone(), e.prev_velocities().clone(), e.launch_count))
     for o in outs[1:]:
         assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]) and torch.equal(o[2], outs[0][2])
     assert outs[0][3] == outs[1][3] == outs[2][3] == 4
+
+
+def test_setters_drop_a_captured_rollout(dev):
+    """A captured graph bakes in device pointers and constants; every setter that changes one of them must
+    drop it, and launching then fails loudly instead of replaying over freed / stale memory."""
+    from silver2_isaacsim_b200 import _lib as L
+
+    wl = W.hexapod_envs(64)
+    e = _engine(wl, torch.float32, dev)
+    ten = [_t(a, torch.float32, dev) for a in (wl.pos, wl.quat_xyzw, wl.lin_vel, wl.ang_vel)]
+    e.bind(*ten, robot_wrench=True)
+    table2 = np.asarray(wl.table, dtype=np.float64) * 1.5
+    setters = [
+        lambda: e.set_part_table(table2, wl.slot_type),
+        lambda: e.set_params_per_body(wl.coeff_per_body()),
+        lambda: e.set_globals(1000.0, 9.8),
+        lambda: e.set_environment((0.1, 0.0, 0.0), 0.2),
+        lambda: e.set_added_mass_dense(np.eye(6)),
+        lambda: e.set_added_mass_dense(None),
+        lambda: e.set_articulation(19),
+        lambda: e.set_articulation_offsets([0, 19, wl.n]),
+        lambda: e.set_kernel("direct"),
+        lambda: e.set_tile_config(0),
+        lambda: e.enable_stats(True),
+        lambda: setattr(e, "quat_order", "wxyz"),
+        lambda: e.set_rollout_mode(False),
+        lambda: e.set_surface_heights(torch.zeros(wl.n, device=dev)),
+    ]
+    for k, setter in enumerate(setters):
+        if k == 8:  # unequal robots changed the wrench shape: bind again with equal runs
+            e.set_articulation(19)
+            e.bind(*ten, robot_wrench=True)
+        e.capture_rollout(2, wl.dt)
+        e.launch_rollout()
+        setter()
+        with pytest.raises(L.H2OError, match="NOT_CONFIGURED"):
+            e.launch_rollout()
+    torch.cuda.synchronize()
+
+
+def test_capture_leaves_state_alone(dev):
+    """Capturing a free-body rollout launches nothing: pose, velocities and carried velocities are untouched."""
+    wl = W.uniform_small_batch(256)
+    e = _engine(wl, torch.float64, dev)
+    ten = [_t(a, torch.float64, dev) for a in (wl.pos, wl.quat_xyzw, wl.lin_vel, wl.ang_vel)]
+    before = [t.clone() for t in ten]
+    e.set_prev(_t(wl.prev_lin, torch.float64, dev), _t(wl.prev_ang, torch.float64, dev))
+    prev0 = e.prev_velocities().clone()
+    e.bind(*ten)
+    e.set_rollout_mode(free_bodies=True, gravity=wl.g)
+    e.capture_rollout(5, wl.dt)
+    torch.cuda.synchronize()
+    assert e.launch_count == 0
+    assert all(torch.equal(a, b) for a, b in zip(ten, before)) and torch.equal(e.prev_velocities(), prev0)
+    e.launch_rollout()
+    torch.cuda.synchronize()
+    assert e.launch_count == 10 and not torch.equal(ten[0], before[0])
 
 
 def test_step_host_pipeline(oracle, dev):
@@ -541,7 +599,7 @@ def test_graph_rollout_with_robot_wrench(oracle, dev):
     e = _engine(wl, torch.float32, dev)
     ten = [_t(a, torch.float32, dev) for a in (wl.pos, wl.quat_xyzw, wl.lin_vel, wl.ang_vel)]
     F, T, Wr = e.bind(*ten, robot_wrench=True)
-    e.capture_rollout(3, wl.dt)      # one eager step, then the 3 captured ones
+    e.capture_rollout(4, wl.dt)
     Wr.fill_(777.0)
     e.launch_rollout()
     torch.cuda.synchronize()
