@@ -89,6 +89,26 @@ def max_over_ranks(value: float, device: Optional[torch.device] = None) -> float
     return float(t.item())
 
 
+def min_over_ranks(value: float, device: Optional[torch.device] = None) -> float:
+    if not dist.is_initialized():
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device or _default_device())
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return float(t.item())
+
+
+def max_over_ranks_vec(values, device: Optional[torch.device] = None):
+    """Element-wise max over ranks of a vector of timings (one entry per timed region)."""
+    import numpy as np
+
+    v = np.asarray(values, dtype=np.float64)
+    if not dist.is_initialized():
+        return v
+    t = torch.as_tensor(v, dtype=torch.float64).to(device or _default_device())
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.cpu().numpy()
+
+
 def sum_over_ranks(value: float, device: Optional[torch.device] = None) -> float:
     if not dist.is_initialized():
         return float(value)

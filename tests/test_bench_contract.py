@@ -7,9 +7,16 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_reference_arm_line(oracle):
+import pytest
+
+
+@pytest.mark.parametrize("kind", ["port", "auto"])
+def test_reference_arm_line(oracle, kind):
+    """--impl reference: the unmodified Numba reference (live tree or the bytecode staged in oracle/_ref)
+    when it is available, else the C port; either way one JSON line on the B200 arm's config."""
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3",
-                          "--warmup", "1", "--bodies-per-gpu", "65536"], capture_output=True, text=True, timeout=300)
+                          "--warmup", "1", "--bodies-per-gpu", "65536", "--ref-kind", kind],
+                         capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-1500:]
     lines = [l for l in res.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -19,7 +26,10 @@ def test_reference_arm_line(oracle):
         assert key in d, key
     assert d["impl"] == "reference" and d["metric"] == "body-force updates/sec" and d["unit"] == "bodies/s"
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and "workload" in d["config"]
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    from oracle import ref_numba
+    want = "reference" if (kind == "auto" and ref_numba.available()) else "port"
+    assert d["cpu_baseline"]["kind"] == want and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["config"]["bodies_per_gpu"] == 65536 and d["steps"] == 3  # the B200 arm's config, not a capped one
     assert d["e2e"] == {"value": d["value"], "unit": "bodies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["value"] > 1e5 and d["gpu_launches"] == 0
 

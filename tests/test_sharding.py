@@ -50,8 +50,11 @@ WORKER = textwrap.dedent("""
     g = sharding.allreduce_stats(stats)
     tmax = sharding.max_over_ranks(1.0 + rank)
     tsum = sharding.sum_over_ranks(float(sh.n_bodies))
+    tmin = sharding.min_over_ranks(1.0 + rank)
+    # per-region timing vectors of bench.py: element-wise max over ranks
+    tvec = sharding.max_over_ranks_vec([1.0 + rank, 5.0 - 3 * rank, 2.0]).tolist()
     sharding.barrier()
-    out = dict(rank=rank, start=sh.robot_start, count=sh.n_robots, g=g, tmax=tmax, tsum=tsum,
+    out = dict(rank=rank, start=sh.robot_start, count=sh.n_robots, g=g, tmax=tmax, tsum=tsum, tmin=tmin, tvec=tvec,
                wrench_sum=wr.sum(axis=0).tolist())
     json.dump(out, open(os.path.join(%(tmp)r, f"rank{rank}.json"), "w"))
     dist.destroy_process_group()
@@ -78,6 +81,7 @@ def test_gloo_world_size_2(tmp_path, oracle):
     for o in outs:
         g = o["g"]
         assert g["bodies"] == wl.n and o["tsum"] == wl.n and o["tmax"] == 2.0
+        assert o["tmin"] == 1.0 and o["tvec"] == [2.0, 5.0, 2.0]
         assert abs(g["sum_force_norm"] - norms.sum()) <= 1e-9 * norms.sum()
         assert g["max_force_norm"] == norms.max()
         assert g["wet_bodies"] == int((r.components["sub_ratio"] > 0).sum())
