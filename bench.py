@@ -857,6 +857,7 @@ def run_b200(args):
                         "ms_per_step_p90": pctl(ms_regions, 90) / args.steps,
                         "ms_per_step_first_region": float(ms_regions[0]) / args.steps,
                         "ms_per_step_mean": float(ms_regions.mean()) / args.steps,
+                        "us_per_step_by_region": [round(1e3 * float(x) / args.steps, 2) for x in ms_regions],
                         "note": "ms_per_step / value / roofline use the MEDIAN region (max over ranks per region)"}}
     # all ranks: BASELINE config 4, strong scaling with the per-robot wrench
     if not args.no_extra and dtype == torch.float32:

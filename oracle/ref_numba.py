@@ -6,7 +6,7 @@ Two places the reference can come from:
 
   live    /root/reference/src/scripts/physics/{numba_hydrodynamics,numba_hydrodynamics_wrapper}.py,
           imported in place (build container only -- the tree does not exist on the GPU box);
-  staged  oracle/_ref/physics/*.pyc, the same two modules byte-compiled from where they lie by
+  staged  oracle/_ref/physics/*.bc, the same two modules byte-compiled from where they lie by
           ``oracle/stage_reference.py`` (git-ignored build artefact that travels to the GPU box).
 
 Uses: (1) validate the C restatement ``hydro_oracle.c`` and generate ``tests/golden`` (here),
@@ -41,8 +41,8 @@ def live_available() -> bool:
 
 
 def staged_available() -> bool:
-    return os.path.isfile(os.path.join(_STAGED, "physics", "numba_hydrodynamics.pyc")) and \
-        os.path.isfile(os.path.join(_STAGED, "physics", "numba_hydrodynamics_wrapper.pyc"))
+    return os.path.isfile(os.path.join(_STAGED, "physics", "numba_hydrodynamics.bc")) and \
+        os.path.isfile(os.path.join(_STAGED, "physics", "numba_hydrodynamics_wrapper.bc"))
 
 
 def available() -> bool:
@@ -69,10 +69,8 @@ def load():
     os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/h2o_numba_cache")  # never inside either tree
     import numba
 
-    base = _SCRIPTS if src == "live" else _STAGED
     old_flag = sys.dont_write_bytecode
     sys.dont_write_bytecode = True  # no __pycache__ in the read-only reference tree
-    sys.path.insert(0, base)
     real_njit = numba.njit
 
     def njit_without_disk_cache(*args, **kwargs):
@@ -80,17 +78,50 @@ def load():
         return real_njit(*args, **kwargs)
 
     numba.njit = njit_without_disk_cache
+    for name in ("physics", "physics.numba_hydrodynamics", "physics.numba_hydrodynamics_wrapper"):
+        sys.modules.pop(name, None)
     try:
-        for name in ("physics", "physics.numba_hydrodynamics", "physics.numba_hydrodynamics_wrapper"):
-            sys.modules.pop(name, None)
-        from physics.numba_hydrodynamics import solve_hydrodynamics  # type: ignore
-        from physics.numba_hydrodynamics_wrapper import NumbaHydrodynamicsWrapper  # type: ignore
+        if src == "live":
+            sys.path.insert(0, _SCRIPTS)
+            try:
+                from physics.numba_hydrodynamics import solve_hydrodynamics  # type: ignore
+                from physics.numba_hydrodynamics_wrapper import NumbaHydrodynamicsWrapper  # type: ignore
+            finally:
+                sys.path.remove(_SCRIPTS)
+        else:
+            mods = _import_staged()
+            solve_hydrodynamics = mods["numba_hydrodynamics"].solve_hydrodynamics
+            NumbaHydrodynamicsWrapper = mods["numba_hydrodynamics_wrapper"].NumbaHydrodynamicsWrapper
     finally:
         numba.njit = real_njit
-        sys.path.remove(base)
         sys.dont_write_bytecode = old_flag
     _loaded = (NumbaHydrodynamicsWrapper, solve_hydrodynamics)
     return _loaded
+
+
+def _import_staged():
+    """What CPython's sourceless import does with a .pyc, for the two staged modules: unmarshal the code
+    object behind the 16-byte header and execute it in a module of the package ``physics`` (the wrapper
+    imports ``.numba_hydrodynamics`` relatively)."""
+    import marshal
+    import types
+
+    pkg = types.ModuleType("physics")
+    pkg.__path__ = []  # a package, with nothing importable from disk
+    sys.modules["physics"] = pkg
+    out = {}
+    for m in ("numba_hydrodynamics", "numba_hydrodynamics_wrapper"):
+        with open(os.path.join(_STAGED, "physics", m + ".bc"), "rb") as f:
+            blob = f.read()
+        code = marshal.loads(blob[16:])
+        mod = types.ModuleType("physics." + m)
+        mod.__package__ = "physics"
+        mod.__file__ = code.co_filename
+        sys.modules["physics." + m] = mod
+        setattr(pkg, m, mod)
+        exec(code, mod.__dict__)
+        out[m] = mod
+    return out
 
 
 def components_via_wrapper(ctor_rows, pos, quat_xyzw, lin_vel, ang_vel, lin_acc, ang_acc,

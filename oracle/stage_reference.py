@@ -8,11 +8,13 @@ from its sources where they lie into ``oracle/_ref/*.so``, the two Python module
     /root/reference/src/scripts/physics/numba_hydrodynamics.py          (the seven @njit functions)
     /root/reference/src/scripts/physics/numba_hydrodynamics_wrapper.py  (NumbaHydrodynamicsWrapper)
 
-are byte-compiled from where they lie into ``oracle/_ref/physics/*.pyc`` (CPython bytecode, no
-source text).  ``oracle/_ref/`` is git-ignored (kept out of history) but not gpurun-ignored, so the
+are byte-compiled from where they lie into ``oracle/_ref/physics/*.bc`` (CPython bytecode in the
+``.pyc`` container format, no source text; the extension is not ``.pyc`` because repository snapshots
+commonly drop ``*.pyc`` / ``__pycache__`` -- the gpurun snapshot does).  ``oracle/_ref/`` is git-ignored (kept out of history) but not gpurun-ignored, so the
 compiled modules travel to the B200 box exactly like the in-tree ``.so`` files.  Nothing is
 modified: the code objects are what CPython would build from the untouched files, and Numba JITs
-from bytecode.  ``oracle/ref_numba.py`` imports them when ``/root/reference`` is absent.
+from bytecode.  ``oracle/ref_numba.py`` loads them (marshal + exec, exactly what CPython's sourceless import does) when
+``/root/reference`` is absent.
 
     python -m oracle.stage_reference          # (re)stage; no-op without /root/reference
 """
@@ -46,7 +48,7 @@ def stage(root: str | None = None, quiet: bool = False) -> bool:
                 "modules": {}}
     for m in MODULES:
         src = os.path.join(src_dir, m + ".py")
-        dst = os.path.join(out_dir, m + ".pyc")
+        dst = os.path.join(out_dir, m + ".bc")
         # dfile: the path shown in tracebacks; keep the reference's own location
         py_compile.compile(src, cfile=dst, dfile=src, doraise=True,
                            invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
@@ -66,7 +68,7 @@ def stage(root: str | None = None, quiet: bool = False) -> bool:
 
 
 def staged() -> bool:
-    return all(os.path.isfile(os.path.join(REF_DIR, "physics", m + ".pyc")) for m in MODULES)
+    return all(os.path.isfile(os.path.join(REF_DIR, "physics", m + ".bc")) for m in MODULES)
 
 
 if __name__ == "__main__":
