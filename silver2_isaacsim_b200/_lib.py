@@ -27,7 +27,7 @@ LAYOUT_SPLIT, LAYOUT_PHYSX, LAYOUT_VIEW = 0, 1, 2
 N_COEFF = 11
 N_STATS = 8
 STATS_FIELDS = ("sum_force_norm", "max_force_norm", "wet_bodies", "clamped_bodies",
-                "nonfinite_bodies", "still_wet_bodies", "bodies", "reserved")
+                "nonfinite_bodies", "still_wet_bodies", "bodies", "reevaluated_bodies")
 
 
 class H2OError(RuntimeError):

@@ -99,6 +99,7 @@ struct h2o_engine {
     void* hp_pin[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaStream_t hp_stream[HOST_PIPE_STREAMS] = {nullptr, nullptr, nullptr};
     cudaStream_t capture_stream = nullptr;  // graph capture never runs on the caller's (maybe legacy) stream
+    int no_fallback = 0;       // study knob (H2O_NO_FALLBACK=1): flagged bodies keep their fast-path result
     bool dry_run = false;  // launch helpers do their one-time attribute / occupancy set-up and count, but launch nothing
 };
 
@@ -444,6 +445,7 @@ static int step_device(h2o_engine* e, int layout, const void* pos, const void* q
     a.surface_z = e->surface_z;
     a.am_dense = e->am_dense; a.am_slot_type = e->am_slot_type; a.am_n_slots = e->am_slots;
     a.robot_offsets = e->robot_offsets; a.n_robots_var = e->n_robots_var;
+    a.no_fallback = e->no_fallback;
     a.surface_eta = e->surface_eta ? static_cast<const char*>(e->surface_eta) + size_t(first_body) * e->esz : nullptr;
     return e->dtype == H2O_F32 ? step_typed<float>(e, layout, a, stream) : step_typed<double>(e, layout, a, stream);
 }
@@ -502,6 +504,7 @@ int h2o_create(h2o_handle* out, int64_t n_bodies, int dtype, int device)
     e->sm_count = prop.multiProcessorCount;
     if (const char* v = getenv("H2O_MAX_CTAS_PER_SM")) e->max_ctas_per_sm = atoi(v);
     if (const char* v = getenv("H2O_PDL")) e->use_pdl = atoi(v) != 0;
+    if (const char* v = getenv("H2O_NO_FALLBACK")) e->no_fallback = atoi(v) != 0;
     if (const char* v = getenv("H2O_ROBOT_CFG")) e->robot_cfg = std::max(-1, std::min(2, atoi(v)));
     if (cudaMalloc(&e->prev, size_t(n_bodies) * 6 * e->esz) != cudaSuccess ||
         cudaMalloc(reinterpret_cast<void**>(&e->stats), N_STATS * sizeof(double)) != cudaSuccess ||

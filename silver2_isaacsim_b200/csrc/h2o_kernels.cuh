@@ -37,7 +37,7 @@ enum : int { PARAM_TABLE = 0, PARAM_PER_BODY = 1 };
 constexpr int N_COEFF = 11;
 constexpr int MAX_TABLE_TYPES = 64;
 constexpr int MAX_TABLE_SLOTS = 256;
-constexpr int N_STATS = 8;  // sum|F|, max|F|, wet, clamped, nonfinite, still, bodies, (spare)
+constexpr int N_STATS = 8;  // sum|F|, max|F|, wet, clamped, nonfinite, still, bodies, re-evaluated in float64
 
 struct StepArgs {
     // LAYOUT_SPLIT: pos (N,3), quat (N,4), lin (N,3), ang (N,3)
@@ -78,6 +78,7 @@ struct StepArgs {
     // nullptr = equal runs of bodies_per_robot.  Wrenches then come from robot_wrench_kernel.
     const long long* robot_offsets;
     long long n_robots_var;
+    int no_fallback;         // study knob (H2O_NO_FALLBACK=1): keep the fast-path result of flagged bodies
 };
 
 // ---------------------------------------------------------------------------
@@ -253,60 +254,122 @@ __device__ __forceinline__ void make_body_in(const RawBody<S>& r, const S* c, in
 // Running statistics kept in registers across a thread's bodies.
 struct ThreadStats {
     double sum_f = 0.0, max_f = 0.0;
-    unsigned wet = 0, clamped = 0, nonfinite = 0, still = 0, bodies = 0;
+    unsigned wet = 0, clamped = 0, nonfinite = 0, still = 0, bodies = 0, redone = 0;
 };
 
-// fp32 mode, quaternion further from unit than fast_path_valid() allows: out-of-line world-frame
-// evaluation (exact in dq, like fp64 mode), so that fp32 mode follows the reference for ANY q.
-// Everything crosses the call by value, so the fast path keeps its registers.
-struct GeneralStepOut {
+// fp32 mode, bodies the fast path flags as ill-conditioned (body_wrench_fast: cancelling torque / force
+// groups, quaternion far from unit): out-of-line float64 re-evaluation with the world-frame formulation
+// (body_terms + net_wrench, the fp64-mode arithmetic), so that fp32 mode meets its bound for EVERY body.
+// A few bodies per 10 000: the function re-reads the body's inputs from global memory instead of keeping
+// thirty scalars alive across the fast path (the hot path keeps its registers), and is never inlined.
+struct ExactStepOut {
     float F[3], T[3];
     float ratio;
     int flags;  // bit 0 clamped, bit 1 still
 };
-__device__ __noinline__ GeneralStepOut body_step_general_f32(
-    double pz, double qx, double qy, double qz, double qw, float vx, float vy, float vz, float wx, float wy, float wz,
-    float ax, float ay, float az, float bx, float by, float bz, float dimx, float dimy, float dimz, float c_drag,
-    float c_drag_ang, float k_damp, float k_damp_ang, float c_am, float c_am_ang, float c_lift, float mass,
-    double rho, double grav, const float* am_dense)
+template <int kLayout, int kParam>
+__device__ __noinline__ ExactStepOut body_step_exact_f32(const StepArgs& a, long long i, double surface_z)
 {
-    BodyIn<double, float> g;
-    g.pz = pz; g.qx = qx; g.qy = qy; g.qz = qz; g.qw = qw;
-    g.vx = vx; g.vy = vy; g.vz = vz; g.wx = wx; g.wy = wy; g.wz = wz;
-    g.ax = ax; g.ay = ay; g.az = az; g.bx = bx; g.by = by; g.bz = bz;
-    g.acc_scale = 1.0f;
-    g.dimx = dimx; g.dimy = dimy; g.dimz = dimz;
-    g.c_drag = c_drag; g.c_drag_ang = c_drag_ang; g.k_damp = k_damp; g.k_damp_ang = k_damp_ang;
-    g.c_am = c_am; g.c_am_ang = c_am_ang; g.c_lift = c_lift;
+    BodyPtrs<float> bp;
+    bp.pos = reinterpret_cast<const float*>(a.pos);
+    bp.quat = reinterpret_cast<const float*>(a.quat);
+    bp.lin = reinterpret_cast<const float*>(a.lin);
+    bp.ang = reinterpret_cast<const float*>(a.ang);
+    bp.prev = reinterpret_cast<const float*>(a.prev);
+    bp.coeff = reinterpret_cast<const float*>(a.coeff);
+    RawBody<float> r;
+    load_raw<float, kLayout>(bp, i, r);
+    const float* c = bp.coeff + N_COEFF * (kParam == PARAM_PER_BODY ? i : (long long)a.slot_type[(a.first_body + i) % a.n_slots]);
+    BodyIn<double, double> g;
+    g.pz = double(r.pz) - surface_z;
+    if (a.quat_wxyz) { g.qx = r.q1; g.qy = r.q2; g.qz = r.q3; g.qw = r.q0; }
+    else { g.qx = r.q0; g.qy = r.q1; g.qz = r.q2; g.qw = r.q3; }
+    // flow-relative velocity: the fast path forms it in fp32 (make_body_in), and so does this
+    g.vx = double(r.vx - float(a.current[0])); g.vy = double(r.vy - float(a.current[1])); g.vz = double(r.vz - float(a.current[2]));
+    g.wx = r.wx; g.wy = r.wy; g.wz = r.wz;
+    g.ax = (double(r.vx) - double(r.pvx)) * a.inv_dt; g.ay = (double(r.vy) - double(r.pvy)) * a.inv_dt;
+    g.az = (double(r.vz) - double(r.pvz)) * a.inv_dt;
+    g.bx = (double(r.wx) - double(r.pwx)) * a.inv_dt; g.by = (double(r.wy) - double(r.pwy)) * a.inv_dt;
+    g.bz = (double(r.wz) - double(r.pwz)) * a.inv_dt;
+    g.acc_scale = 1.0;
+    g.dimx = c[0]; g.dimy = c[1]; g.dimz = c[2];
+    g.c_drag = c[3]; g.c_drag_ang = c[4]; g.k_damp = c[5]; g.k_damp_ang = c[6];
+    g.c_am = c[7]; g.c_am_ang = c[8]; g.c_lift = c[9];
     g.warp_compat = false;
-    g.rho_h = rho; g.grav_h = grav; g.rho = float(rho);
-    g.am_dense = am_dense;
-    Terms<double, float> t;
-    body_terms<double, float, false>(g, t);
-    GeneralStepOut o;
+    g.rho_h = a.rho; g.grav_h = a.grav; g.rho = double(float(a.rho));  // L constants as the fast path rounds them
+    double md[36];
+    g.am_dense = nullptr;
+    if (a.am_dense) {
+        const float* m = reinterpret_cast<const float*>(a.am_dense) + 36 * a.am_slot_type[(a.first_body + i) % a.am_n_slots];
+        for (int k = 0; k < 36; ++k) md[k] = double(m[k]);
+        g.am_dense = md;
+    }
+    Terms<double, double> t;
+    body_terms<double, double, false>(g, t);
+    double F[3], T[3];
     bool clamped;
-    net_wrench<double, float>(t, mass, o.F, o.T, clamped);
+    net_wrench<double, double>(t, double(c[10]), F, T, clamped);
+    ExactStepOut o;
+    for (int k = 0; k < 3; ++k) {
+        o.F[k] = float(F[k]);
+        o.T[k] = float(T[k]);
+    }
     o.ratio = float(t.ratio);
     o.flags = (clamped ? 1 : 0) | (t.still ? 2 : 0);
     return o;
 }
 
-// fp32 mode: body-frame fast path; fp64 mode: the world-frame formulation (exact in dq).
+// fp32 mode: body-frame fast path (returns true when the body must be re-evaluated, see above);
+// fp64 mode: the world-frame formulation (exact in dq).
 template <typename S>
-__device__ __forceinline__ void body_step(const BodyIn<double, S>& in, S mass, S F[3], S T[3],
-                                          ThreadStats* st)
+__device__ __forceinline__ bool body_step(const BodyIn<double, S>& in, S mass, S F[3], S T[3], bool& clamped,
+                                          bool& still, double& ratio)
+{
+    if (sizeof(S) == 4) {
+        bool suspect;
+        body_wrench_fast<double, S>(in, mass, F, T, clamped, ratio, still, suspect);
+        return suspect;
+    } else {
+        Terms<double, S> t;
+        body_terms<double, S, false>(in, t);
+        net_wrench<double, S>(t, mass, F, T, clamped);
+        ratio = t.ratio;
+        still = t.still;
+        return false;
+    }
+}
+
+__device__ __forceinline__ void accumulate_stats(ThreadStats& st, double fx, double fy, double fz, double ratio,
+                                                 bool clamped, bool still, bool redone)
+{
+    const double mag = sqrt(fx * fx + fy * fy + fz * fz);
+    st.bodies += 1;
+    if (mag == mag && mag < 1.7e308) {
+        st.sum_f += mag;
+        st.max_f = fmax(st.max_f, mag);
+    } else {
+        st.nonfinite += 1;
+    }
+    st.wet += (ratio > 0.0) ? 1u : 0u;
+    st.clamped += clamped ? 1u : 0u;
+    st.still += (ratio > 0.0 && still) ? 1u : 0u;
+    st.redone += redone ? 1u : 0u;
+}
+
+// One body of a step kernel: fast path, float64 re-evaluation when flagged (fp32 mode), statistics.
+// `i` = body index inside the launch (a.pos etc. are the launch's base pointers).
+template <typename S, int kLayout, int kParam, bool kStats>
+__device__ __forceinline__ void step_one_body(const StepArgs& a, long long i, const BodyIn<double, S>& in, S mass,
+                                              double surface_z, S F[3], S T[3], ThreadStats& st)
 {
     bool clamped, still;
     double ratio;
+    bool redo = body_step<S>(in, mass, F, T, clamped, still, ratio);
     if (sizeof(S) == 4) {
-        if (!fast_path_valid(in)) {
-            const float sc = float(in.acc_scale);
-            const GeneralStepOut o = body_step_general_f32(
-                in.pz, in.qx, in.qy, in.qz, in.qw, float(in.vx), float(in.vy), float(in.vz), float(in.wx), float(in.wy),
-                float(in.wz), float(in.ax) * sc, float(in.ay) * sc, float(in.az) * sc, float(in.bx) * sc,
-                float(in.by) * sc, float(in.bz) * sc, float(in.dimx), float(in.dimy), float(in.dimz), float(in.c_drag),
-                float(in.c_drag_ang), float(in.k_damp), float(in.k_damp_ang), float(in.c_am), float(in.c_am_ang),
-                float(in.c_lift), float(mass), in.rho_h, in.grav_h, reinterpret_cast<const float*>(in.am_dense));
+        redo = redo && !a.no_fallback;
+        if (redo) {
+            const ExactStepOut o = body_step_exact_f32<kLayout, kParam>(a, i, surface_z);
+#pragma unroll
             for (int k = 0; k < 3; ++k) {
                 F[k] = S(o.F[k]);
                 T[k] = S(o.T[k]);
@@ -314,29 +377,9 @@ __device__ __forceinline__ void body_step(const BodyIn<double, S>& in, S mass, S
             ratio = double(o.ratio);
             clamped = (o.flags & 1) != 0;
             still = (o.flags & 2) != 0;
-        } else {
-            body_wrench_fast<double, S>(in, mass, F, T, clamped, ratio, still);
         }
-    } else {
-        Terms<double, S> t;
-        body_terms<double, S, false>(in, t);
-        net_wrench<double, S>(t, mass, F, T, clamped);
-        ratio = t.ratio;
-        still = t.still;
     }
-    if (st) {
-        const double mag = sqrt(double(F[0]) * double(F[0]) + double(F[1]) * double(F[1]) + double(F[2]) * double(F[2]));
-        st->bodies += 1;
-        if (mag == mag && mag < 1.7e308) {
-            st->sum_f += mag;
-            st->max_f = fmax(st->max_f, mag);
-        } else {
-            st->nonfinite += 1;
-        }
-        st->wet += (ratio > 0.0) ? 1u : 0u;
-        st->clamped += clamped ? 1u : 0u;
-        st->still += (ratio > 0.0 && still) ? 1u : 0u;
-    }
+    if (kStats) accumulate_stats(st, double(F[0]), double(F[1]), double(F[2]), ratio, clamped, still, redo);
 }
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -360,7 +403,7 @@ __device__ __forceinline__ void flush_stats(const ThreadStats& st, double* stats
     const double s = warp_sum(st.sum_f);
     const double m = warp_max(st.max_f);
     const unsigned wet = warp_sum_u(st.wet), cl = warp_sum_u(st.clamped), nf = warp_sum_u(st.nonfinite),
-                   sl = warp_sum_u(st.still), nb = warp_sum_u(st.bodies);
+                   sl = warp_sum_u(st.still), nb = warp_sum_u(st.bodies), rd = warp_sum_u(st.redone);
     if ((threadIdx.x & 31) == 0 && nb) {
         atomicAdd(&stats[0], s);
         // max of non-negative doubles == max of their bit patterns
@@ -371,6 +414,7 @@ __device__ __forceinline__ void flush_stats(const ThreadStats& st, double* stats
         atomicAdd(&stats[4], double(nf));
         atomicAdd(&stats[5], double(sl));
         atomicAdd(&stats[6], double(nb));
+        atomicAdd(&stats[7], double(rd));
     }
 }
 
@@ -568,7 +612,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
             } else {
                 BodyIn<double, S> bin;
                 make_body_in<S>(r, cl, a.quat_wxyz, a.rho, a.grav, inv_dt, env, bin);
-                body_step<S>(bin, cl[10], F, T, kStats ? &st : nullptr);
+                step_one_body<S, kLayout, kParam, kStats>(a, tile_begin + tid, bin, cl[10], env.surface_z, F, T, st);
             }
 
             using V2 = typename Vec2Of<S>::type;
@@ -681,7 +725,7 @@ __global__ void __launch_bounds__(256) step_direct_kernel(const __grid_constant_
         if (a.am_dense)
             bin.am_dense = reinterpret_cast<const S*>(a.am_dense) + 36 * a.am_slot_type[(a.first_body + i) % a.am_n_slots];
         S F[3], T[3];
-        body_step<S>(bin, cl[10], F, T, kStats ? &st : nullptr);
+        step_one_body<S, kLayout, kParam, kStats>(a, i, bin, cl[10], env.surface_z, F, T, st);
         S* of = reinterpret_cast<S*>(a.out_force) + 3 * i;
         S* ot = reinterpret_cast<S*>(a.out_torque) + 3 * i;
         of[0] = F[0]; of[1] = F[1]; of[2] = F[2];

@@ -189,11 +189,10 @@ template <typename H, typename L> struct BodyIn {
 // q, so its R is orthogonal only up to dq = |q|^2 - 1.  Quaternions handed out by a simulator are unit to
 // fp32 rounding (|dq| <= 2.4e-7); anything further from unit must take body_terms + net_wrench (exact in dq).
 constexpr double FAST_PATH_MAX_DQ = 1e-6;
-template <typename H, typename L> H2O_HD bool fast_path_valid(const BodyIn<H, L>& in)
-{
-    const H dq = ((in.qx * in.qx + in.qy * in.qy) + (in.qz * in.qz + in.qw * in.qw)) - H(1);
-    return !(h2o_abs(dq) > H(FAST_PATH_MAX_DQ));
-}
+// Conditioning thresholds of body_wrench_fast (see there), chosen with tests/harness/flag_study.py: of 1.4e7
+// random wet bodies (C2 / C3 / C4 distributions) no unflagged one comes closer than 0.65x to the fp32-mode
+// bound; 2.5e-4 (C3) / 3e-5 (hexapod fleets) of the bodies are flagged.
+constexpr double FLAG_KAPPA_T = 0.06, FLAG_KAPPA_F = 0.15;
 
 template <typename H, typename L> struct Terms {
     H ratio;              // submersion ratio (0 => every other field is 0)
@@ -485,7 +484,7 @@ H2O_HD void net_wrench(const Terms<H, L>& t, L mass, L F[3], L T[3], bool& clamp
 // ---------------------------------------------------------------------------
 template <typename H, typename L>
 H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], bool& clamped, H& ratio_out,
-                             bool& still)
+                             bool& still, bool& suspect, L* diag = nullptr)
 {
     // ---- waterline in H (identical to body_terms)
     const H hx2 = in.qx + in.qx, hy2 = in.qy + in.qy, hz2 = in.qz + in.qz;
@@ -579,11 +578,14 @@ H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], boo
     const L speed = h2o_sqrt_from_rsqrt(speed2, rs);
     const bool moving = speed > L(1e-6);
     const L inv_speed = moving ? rs : L(0);
-    const L ux = in.vx * inv_speed, uy = in.vy * inv_speed, uz = in.vz * inv_speed;
     still = !moving && (ratio > H(0));
-    const L d0 = r00 * ux + r10 * uy + r20 * uz;
-    const L d1 = r01 * ux + r11 * uy + r21 * uz;
-    const L d2 = r02 * ux + r12 * uy + r22 * uz;
+    // d = R^T v_hat carried in H: when the flow is nearly parallel to a face, d_j is a cancelled sum of O(1)
+    // products and the centre of pressure is a RATIO of such alignments; L products of an L-rounded R lose
+    // it (1e-5 relative on the drag lever arm for alignments ~1e-3).  All nine H entries of R exist already.
+    const H vxh = H(in.vx), vyh = H(in.vy), vzh = H(in.vz);
+    const L d0 = L((H(1) - (hyy + hzz)) * vxh + (hxy + hwz) * vyh + r20h * vzh) * inv_speed;
+    const L d1 = L((hxy - hwz) * vxh + (H(1) - (hxx + hzz)) * vyh + r21h * vzh) * inv_speed;
+    const L d2 = L((hxz + hwy) * vxh + (hyz - hwx) * vyh + r22h * vzh) * inv_speed;
 
     // ---- projected area, centre of pressure (body frame) -- see body_terms
     const uint32_t f0 = (d0 < L(0)) ? (1u << kp_bit(1, 0, 0)) : (1u << kp_bit(-1, 0, 0));
@@ -633,6 +635,8 @@ H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], boo
     const L bby = r01 * in.bx + r11 * in.by + r21 * in.bz;
     const L bbz = r02 * in.bx + r12 * in.by + r22 * in.bz;
     L ml, ffx, ffy, ffz, tbx, tby, tbz;
+    L ai0, ai1, ai2;  // added-inertia torque, body frame
+    const L cfx = army * flz - armz * fly, cfy = armz * flx - armx * flz, cfz = armx * fly - army * flx;  // arm x F_l
     if (in.am_dense) {
         const L a6[6] = {r00 * in.ax + r10 * in.ay + r20 * in.az, r01 * in.ax + r11 * in.ay + r21 * in.az,
                          r02 * in.ax + r12 * in.ay + r22 * in.az, bbx, bby, bbz};
@@ -645,19 +649,18 @@ H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], boo
         }
         ml = L(0);
         ffx = flx - f6[0]; ffy = fly - f6[1]; ffz = flz - f6[2];
-        tbx = psi * tdx + ((army * flz - armz * fly) - f6[3]);
-        tby = psi * tdy + ((armz * flx - armx * flz) - f6[4]);
-        tbz = psi * tdz + ((armx * fly - army * flx) - f6[5]);
+        ai0 = f6[3]; ai1 = f6[4]; ai2 = f6[5];
     } else {
         ml = rv * in.c_am;
         const L ma = rv * in.c_am_ang;
         const L w2s = in.dimx * in.dimx, d2s = in.dimy * in.dimy, h2s = in.dimz * in.dimz;
         ffx = flx; ffy = fly; ffz = flz;
         // ---- body-frame torque: psi*(...) + arm x F_l + added inertia (buoyancy torque: tbuoy, above)
-        tbx = psi * tdx + ((army * flz - armz * fly) - ma * (d2s + h2s) * bbx);
-        tby = psi * tdy + ((armz * flx - armx * flz) - ma * (w2s + h2s) * bby);
-        tbz = psi * tdz + ((armx * fly - army * flx) - ma * (w2s + d2s) * bbz);
+        ai0 = ma * (d2s + h2s) * bbx; ai1 = ma * (w2s + h2s) * bby; ai2 = ma * (w2s + d2s) * bbz;
     }
+    tbx = psi * tdx + (cfx - ai0);
+    tby = psi * tdy + (cfy - ai1);
+    tbz = psi * tdz + (cfz - ai2);
 
     // ---- angular drag (world): -(0.5 rho |w| C V + k min(1, 5|w|)) ratio * w
     const L as2 = in.wx * in.wx + in.wy * in.wy + in.wz * in.wz;
@@ -673,6 +676,43 @@ H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], boo
     F[1] = (r10 * ffx + r11 * ffy + r12 * ffz) - (gam * in.vy + ml * in.ay);
     const L fz = (r20 * ffx + r21 * ffy + r22 * ffz) - (gam * in.vz + ml * in.az);
     F[2] = L(fbz + H(fz));
+
+    // ---- conditioning check.  L arithmetic carries ~1e-7 relative error per TERM; the result meets the
+    // fp32-mode bound (1e-5 relative per vector) unless that error is amplified:
+    //   (a) the torque groups cancel: |T| << sum of the group magnitudes;
+    //   (b) the force groups cancel (buoyancy against drag, mostly);
+    //   (c) the quaternion is further from unit than the body-frame formulation tolerates.
+    // Such bodies (a few per 100 000) are flagged and the caller re-evaluates them in float64 with the
+    // world-frame formulation (body_terms + net_wrench), so fp32 mode stays inside its bound for EVERY body.
+    L flag_kt, flag_kf;
+    {
+        const L mt = ((h2o_abs(psi) * ((h2o_abs(tdx) + h2o_abs(tdy)) + h2o_abs(tdz)) +
+                       ((h2o_abs(cfx) + h2o_abs(cfy)) + h2o_abs(cfz))) +
+                      ((h2o_abs(ai0) + h2o_abs(ai1)) + h2o_abs(ai2))) +
+                     ((ka * ((h2o_abs(in.wx) + h2o_abs(in.wy)) + h2o_abs(in.wz))) + (h2o_abs(tbuoy_x) + h2o_abs(tbuoy_y)));
+        const L t1 = (h2o_abs(T[0]) + h2o_abs(T[1])) + h2o_abs(T[2]);
+        const L f1 = (h2o_abs(F[0]) + h2o_abs(F[1])) + h2o_abs(F[2]);
+        // (b): buoyancy is the only force group that does not vanish with the velocities, so a cancelled net
+        // force means |F| << F_buoyancy
+        flag_kt = t1 / h2o_max(mt, L(1e-30)); flag_kf = f1 / h2o_max(L(fbz), L(1e-30));
+        suspect = (t1 < L(FLAG_KAPPA_T) * mt) | (f1 < L(FLAG_KAPPA_F) * L(fbz)) | (h2o_abs(dqh) > H(FAST_PATH_MAX_DQ));
+    }
+
+    if (diag) {  // precision study only (tests/harness/precision_study.py): magnitudes of the term groups
+        auto mx = [](L a, L b, L c) { return h2o_max(h2o_abs(a), h2o_max(h2o_abs(b), h2o_abs(c))); };
+        diag[0] = h2o_abs(psi) * mx(tdx, tdy, tdz);
+        diag[1] = mx(cfx, cfy, cfz);
+        diag[2] = mx(tbx, tby, tbz);
+        diag[3] = ka * mx(in.wx, in.wy, in.wz);
+        diag[4] = mx(tbuoy_x, tbuoy_y, L(0));
+        diag[5] = mx(T[0], T[1], T[2]);
+        diag[6] = mx(ffx, ffy, ffz);
+        diag[7] = gam * mx(in.vx, in.vy, in.vz);
+        diag[8] = ml * mx(in.ax, in.ay, in.az);
+        diag[9] = L(fbz);
+        diag[10] = mx(F[0], F[1], F[2]);
+        diag[11] = flag_kt; diag[12] = flag_kf; diag[13] = L(0);
+    }
 
     // ---- safety clamp (hydrodynamics_behavior.py:221-226)
     const L max_force = mass * L(500.0);

@@ -11,6 +11,9 @@
 
 using namespace h2o;
 
+static int g_no_fallback = 0;  // precision study: report what the fast path alone would give
+extern "C" __attribute__((visibility("default"))) void emul_set_no_fallback(int v) { g_no_fallback = v; }
+
 template <typename S, typename H, typename L, bool kExactTrig, bool kFast = false>
 static void run(int64_t n, const double* pos, const double* quat, const double* v, const double* w,
                 const double* pl, const double* pa, const double* coeff, double rho, double g,
@@ -52,19 +55,44 @@ static void run(int64_t n, const double* pos, const double* quat, const double* 
         Terms<H, L> t;
         L f[3], tq[3];
         bool clamped;
-        if (kFast && fast_path_valid(in)) {
+        if (kFast) {  // same dispatch as body_step() in h2o_kernels.cuh: fast path, float64 re-evaluation when flagged
             H ratio;
-            bool still;
-            body_wrench_fast<H, L>(in, L(S(c[10])), f, tq, clamped, ratio, still);
-            comp = nullptr;
+            bool still, suspect;
+            L dg[14] = {0};
+            body_wrench_fast<H, L>(in, L(S(c[10])), f, tq, clamped, ratio, still, suspect, comp ? dg : nullptr);
+            if (comp) {  // mode 4 returns the term-group magnitudes where the other modes return components
+                for (int k = 0; k < 14; ++k) comp[28 * i + k] = double(dg[k]);
+                comp[28 * i + 27] = suspect ? 2.0 : 1.0;
+            }
             t.kp_mask = 0;
-        } else if (kFast) {  // same dispatch as body_step() in h2o_kernels.cuh
-            in.ax *= in.acc_scale; in.ay *= in.acc_scale; in.az *= in.acc_scale;
-            in.bx *= in.acc_scale; in.by *= in.acc_scale; in.bz *= in.acc_scale;
-            in.acc_scale = L(1);
-            body_terms<H, L, false>(in, t);
-            net_wrench<H, L>(t, L(S(c[10])), f, tq, clamped);
-            comp = nullptr;
+            if (suspect && !g_no_fallback) {
+                BodyIn<double, double> ex;
+                ex.pz = double(in.pz); ex.qx = double(in.qx); ex.qy = double(in.qy); ex.qz = double(in.qz); ex.qw = double(in.qw);
+                ex.vx = double(in.vx); ex.vy = double(in.vy); ex.vz = double(in.vz);
+                ex.wx = double(in.wx); ex.wy = double(in.wy); ex.wz = double(in.wz);
+                const double isc = 1.0 / dt;
+                ex.ax = (double(in.vx) - double(S(pl[3 * i]))) * isc; ex.ay = (double(in.vy) - double(S(pl[3 * i + 1]))) * isc;
+                ex.az = (double(in.vz) - double(S(pl[3 * i + 2]))) * isc;
+                ex.bx = (double(in.wx) - double(S(pa[3 * i]))) * isc; ex.by = (double(in.wy) - double(S(pa[3 * i + 1]))) * isc;
+                ex.bz = (double(in.wz) - double(S(pa[3 * i + 2]))) * isc;
+                ex.acc_scale = 1.0;
+                ex.dimx = double(in.dimx); ex.dimy = double(in.dimy); ex.dimz = double(in.dimz);
+                ex.c_drag = double(in.c_drag); ex.c_drag_ang = double(in.c_drag_ang); ex.k_damp = double(in.k_damp);
+                ex.k_damp_ang = double(in.k_damp_ang); ex.c_am = double(in.c_am); ex.c_am_ang = double(in.c_am_ang);
+                ex.c_lift = double(in.c_lift); ex.warp_compat = false;
+                ex.rho_h = rho; ex.grav_h = g; ex.rho = rho;
+                double md[36];
+                ex.am_dense = nullptr;
+                if (dense) {
+                    for (int k = 0; k < 36; ++k) md[k] = double(mloc[k]);
+                    ex.am_dense = md;
+                }
+                Terms<double, double> te;
+                double fe[3], qe[3];
+                body_terms<double, double, false>(ex, te);
+                net_wrench<double, double>(te, double(S(c[10])), fe, qe, clamped);
+                for (int k = 0; k < 3; ++k) { f[k] = L(fe[k]); tq[k] = L(qe[k]); }
+            }
         } else {
             body_terms<H, L, kExactTrig>(in, t);
             net_wrench<H, L>(t, L(S(c[10])), f, tq, clamped);
@@ -73,7 +101,7 @@ static void run(int64_t n, const double* pos, const double* quat, const double* 
             F[3 * i + k] = double(S(f[k]));
             T[3 * i + k] = double(S(tq[k]));
         }
-        if (comp) {
+        if (comp && !kFast) {
             double* o = comp + 28 * i;
             o[0] = 0; o[1] = 0; o[2] = double(t.fbz);
             for (int k = 0; k < 3; ++k) {

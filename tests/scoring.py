@@ -33,11 +33,13 @@ def force_scale(coeff, rho, g):
     return rho * g * coeff[:, 0] * coeff[:, 1] * coeff[:, 2]
 
 
-def assert_fp32(x, y, what, min_pass=0.99999, hard_factor=10.0):
-    """Strict criterion for >= min_pass of the vectors; none beyond hard_factor x the tolerance.
+def assert_fp32(x, y, what, min_pass=1.0, hard_factor=1.0):
+    """The north-star bound for EVERY vector: |x-y|_inf <= max(1e-5 |y|_inf, 1e-6), no exceptions.
 
-    The residual (~1e-6 of random bodies) are torques whose large terms cancel by chance;
-    fp32 storage cannot resolve them (measured in tests/harness/precision_study.py).
+    (Round 1 allowed 1e-5 of the vectors up to 10x the bound: torques whose large terms cancel by chance.
+    The fp32 fast path now flags such bodies and re-evaluates them in float64 -- csrc/h2o_model.cuh,
+    body_wrench_fast -- so the defaults are strict; min_pass / hard_factor stay as parameters for the
+    precision studies.)
     """
     err, den = vec_err(x, y)
     tol = np.maximum(FP32_REL * den, FP32_ABS)

@@ -115,8 +115,8 @@ def test_robot_wrench_any_robot_size(oracle, dev, bpr, dtype):
     assert e.last_kernel == "tile"
     ref = _ref(oracle, wl)
     if dtype == torch.float32:
-        scoring.assert_fp32(F, ref.force, f"robots of {bpr} force", min_pass=0.9999)
-        scoring.assert_fp32(T, ref.torque, f"robots of {bpr} torque", min_pass=0.9999)
+        scoring.assert_fp32(F, ref.force, f"robots of {bpr} force")
+        scoring.assert_fp32(T, ref.torque, f"robots of {bpr} torque")
     else:
         _check(wl, dtype, ref, F, T, f"robots of {bpr}")
     want = oracle.robot_wrench(wl.pos, ref.force, ref.torque, bpr)
@@ -148,8 +148,8 @@ def test_part_table_any_slot_map(oracle, dev, kernel, n_slots, n_types):
     assert e.last_kernel == kernel
     ref = oracle.step(P.coeff_to_ctor_rows(coeff, wl.rho, wl.g), coeff[:, 10].copy(), wl.pos, wl.quat_xyzw,
                       wl.lin_vel, wl.ang_vel, wl.prev_lin, wl.prev_ang, wl.dt)
-    scoring.assert_fp32(F, ref.force, "table force", min_pass=0.9999)
-    scoring.assert_fp32(T, ref.torque, "table torque", min_pass=0.9999)
+    scoring.assert_fp32(F, ref.force, "table force")
+    scoring.assert_fp32(T, ref.torque, "table torque")
 
 
 @pytest.mark.parametrize("kernel", ["tile", "direct"])
@@ -167,14 +167,10 @@ def test_stress_distribution_gpu(oracle, dev, dtype, kernel):
     assert e.last_kernel == kernel
     assert np.isfinite(F).all() and np.isfinite(T).all()
     if dtype == torch.float32:
-        okF, okT = scoring.fp32_ok(F, ref.force), scoring.fp32_ok(T, ref.torque)
-        assert okF.mean() >= 0.9999, okF.mean()
-        # world-space lever arms at |p| = 2 km, as the reference computes them, cannot resolve 1e-5 of a
-        # small torque in fp32 storage: score the torque with the survey's |p||F| caveat term
-        err, den = scoring.vec_err(T, ref.torque)
-        pn = np.abs(wl.pos).max(axis=1).astype(float) * np.abs(ref.force).max(axis=1)
-        assert (err <= np.maximum(1e-5 * den, 1e-6) + 2e-7 * pn).mean() >= 0.9999
-        assert okT.mean() >= 0.99, okT.mean()
+        # every quaternion of this set is far from unit: the fast path flags every body and the float64
+        # re-evaluation answers, so the strict bound holds even with |p| = 2 km
+        scoring.assert_fp32(F, ref.force, "stress force")
+        scoring.assert_fp32(T, ref.torque, "stress torque")
     else:
         scale = scoring.force_scale(wl.coeff_per_body(), wl.rho, wl.g)
         assert scoring.fp64_ok(F, ref.force, scale).all()
@@ -220,8 +216,8 @@ def test_unequal_robots_by_offsets(oracle, dev, dtype, kernel):
     assert e.last_kernel == kernel and Wr.shape == (len(sizes), 6)
     ref = _ref(oracle, wl)
     if dtype == torch.float32:
-        scoring.assert_fp32(F, ref.force, "offset robots force", min_pass=0.9999)
-        scoring.assert_fp32(T, ref.torque, "offset robots torque", min_pass=0.9999)
+        scoring.assert_fp32(F, ref.force, "offset robots force")
+        scoring.assert_fp32(T, ref.torque, "offset robots torque")
     else:
         _check(wl, dtype, ref, F, T, "offset robots")
     pos, Fr, Tr = wl.pos.astype(np.float64), ref.force, ref.torque
@@ -282,9 +278,8 @@ def test_random_configurations(oracle, dev):
         ref = oracle.step(P.coeff_to_ctor_rows(coeff, wl.rho, wl.g), coeff[:, 10].copy(), wl.pos, wl.quat_xyzw,
                           wl.lin_vel, wl.ang_vel, wl.prev_lin, wl.prev_ang, wl.dt)
         if dtype == torch.float32:
-            assert scoring.fp32_ok(F, ref.force).mean() >= 0.9995, what
-            assert scoring.fp32_ok(T, ref.torque).mean() >= 0.9995, what
-            assert scoring.fp32_ok(F, ref.force, rel=1e-4).all() and scoring.fp32_ok(T, ref.torque, rel=1e-4).all(), what
+            scoring.assert_fp32(F, ref.force, what + " force")
+            scoring.assert_fp32(T, ref.torque, what + " torque")
         else:
             scale = scoring.force_scale(coeff, wl.rho, wl.g)
             pn = np.abs(wl.pos).max(axis=1).astype(float) * np.abs(ref.force).max(axis=1)
@@ -315,8 +310,8 @@ def test_carried_velocities_over_several_steps(oracle, dev, kernel):
         if dt > 1e-6:
             ref = oracle.step(wl.ctor_rows(), wl.masses(), wl.pos, wl.quat_xyzw, v, w, prev_l, prev_a, dt)
             prev_l, prev_a = ref.prev_lin, ref.prev_ang
-            scoring.assert_fp32(F.cpu().numpy(), ref.force, f"step {k} force", min_pass=0.9999)
-            scoring.assert_fp32(T.cpu().numpy(), ref.torque, f"step {k} torque", min_pass=0.9999)
+            scoring.assert_fp32(F.cpu().numpy(), ref.force, f"step {k} force")
+            scoring.assert_fp32(T.cpu().numpy(), ref.torque, f"step {k} torque")
         got = e.prev_velocities().double().cpu().numpy()
         assert (got[:, :3] == prev_l).all() and (got[:, 3:] == prev_a).all(), k
         v = (v + rng.normal(size=v.shape).astype(np.float32) * 0.05).astype(np.float32)
@@ -569,8 +564,8 @@ def test_step_host_table_slots_and_height_field(oracle, dev):
             pos[:, 2] -= eta.astype(np.float64)
         F, T = e.step_host(wl.pos, wl.quat_xyzw, wl.lin_vel, wl.ang_vel, wl.dt)
         ref = oracle.step(ctor, mass, pos, wl.quat_xyzw, wl.lin_vel, wl.ang_vel, wl.prev_lin, wl.prev_ang, wl.dt)
-        scoring.assert_fp32(F, ref.force, f"step_host table eta={use_eta} force", min_pass=0.9999)
-        scoring.assert_fp32(T, ref.torque, f"step_host table eta={use_eta} torque", min_pass=0.9999)
+        scoring.assert_fp32(F, ref.force, f"step_host table eta={use_eta} force")
+        scoring.assert_fp32(T, ref.torque, f"step_host table eta={use_eta} torque")
 
 
 def test_unaligned_views_are_refused(dev):
@@ -809,8 +804,8 @@ def test_no_out_of_bounds_writes(oracle, dev, n_robots):
         for buf, rows in ((bufF, n), (bufT, n), (bufW, R)):
             assert (buf[:G] == 777.0).all() and (buf[G + rows:] == 777.0).all(), (kernel, n_robots)
         assert not (F == 777.0).all(dim=1).any() and not (Wr == 777.0).all(dim=1).any()  # every row written
-        scoring.assert_fp32(F.cpu().numpy(), ref.force, "guarded force", min_pass=0.999)
-        scoring.assert_fp32(T.cpu().numpy(), ref.torque, "guarded torque", min_pass=0.999)
+        scoring.assert_fp32(F.cpu().numpy(), ref.force, "guarded force")
+        scoring.assert_fp32(T.cpu().numpy(), ref.torque, "guarded torque")
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["fp32", "fp64"])

@@ -73,5 +73,4 @@ def test_stress_fp32_mode(oracle):
     errT, denT = scoring.vec_err(T, ref.torque)
     print(f"stress fp32: force pass {okF.mean():.6f} (worst {np.max(errF / np.maximum(1e-5 * denF, 1e-6)):.2f}x), "
           f"torque pass {okT.mean():.6f} (worst {np.max(errT / np.maximum(1e-5 * denT, 1e-6)):.2f}x)")
-    assert okF.mean() >= 0.9995, okF.mean()
-    assert okT.mean() >= 0.995, okT.mean()
+    assert okF.all() and okT.all()   # non-unit quaternions: every body is re-evaluated in float64
