@@ -64,7 +64,7 @@ typedef enum { H2O_KERNEL_AUTO = 0, H2O_KERNEL_TILE = 1, H2O_KERNEL_DIRECT = 2 }
 #define H2O_N_COEFF 11
 /* h2o_stats vector: sum|F|, max|F|, wet bodies, clamped bodies, non-finite forces,
  * wet-and-at-rest bodies (the reference raises there, numba_hydrodynamics.py:118,143),
- * bodies processed, reserved. */
+ * bodies processed, bodies the fp32 fast path handed to the float64 re-evaluation. */
 #define H2O_N_STATS 8
 
 H2O_API const char* h2o_last_error(void);
@@ -205,6 +205,19 @@ H2O_API int h2o_capture_rollout(h2o_handle h, int n_steps, double dt, h2o_stream
  * pose / velocity tensors are integrated in place by h2o_integrate_free_bodies (split layout). */
 H2O_API int h2o_set_rollout_mode(h2o_handle h, int free_bodies, double gravity);
 H2O_API int h2o_launch_rollout(h2o_handle h, h2o_stream stream);
+
+/* Persistent rollout of FREE bodies over the bound tensors (split layout): n_steps x (fused force step ->
+ * h2o_integrate_free_bodies) in ONE kernel launch, each thread carrying its body's pose, velocities,
+ * previous velocities and coefficients in registers across the steps (bodies are independent:
+ * solve_hydrodynamics reads only its own body, numba_hydrodynamics.py:255-314; the behaviour's per-step
+ * bookkeeping is hydrodynamics_behavior.py:196-238).  Same result as h2o_capture_rollout in free-body mode
+ * (up to FMA contraction) without a launch / graph node per step.  On return of the kernel the bound pose /
+ * velocity tensors and the carried velocities hold the final state, out_force / out_torque the last step's
+ * wrench.  trace_every > 0: every trace_every-th step a row [p, v, w] (9 scalars, handle dtype) per body
+ * goes to trace_out, a device array (n_steps / trace_every, n_bodies, 9) -- the columns of the
+ * reference's velocity logger (log_velocity.py:17-20).  dt <= 1e-6 is a successful no-op. */
+H2O_API int h2o_rollout_persistent(h2o_handle h, int n_steps, double dt, double gravity, int trace_every,
+                                   void* trace_out, h2o_stream stream);
 
 /* ---- stand-alone free-body stepper (harness; the reference leaves integration to PhysX) ------
  * Semi-implicit Euler for free boxes (mass and dimensions from the coefficient records, box

@@ -71,6 +71,7 @@ SIGNATURES = {
     "h2o_unbind": (c_int, [_P]),
     "h2o_step_bound": (c_int, [_P, c_double, _P]),
     "h2o_capture_rollout": (c_int, [_P, c_int, c_double, _P]),
+    "h2o_rollout_persistent": (c_int, [_P, c_int, c_double, c_double, c_int, _P, _P]),
     "h2o_launch_rollout": (c_int, [_P, _P]),
     "h2o_set_rollout_mode": (c_int, [_P, c_int, c_double]),
     "h2o_integrate_free_bodies": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_double, c_double, _P]),

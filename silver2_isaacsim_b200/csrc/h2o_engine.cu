@@ -1109,6 +1109,58 @@ int h2o_launch_rollout(h2o_handle h, h2o_stream stream)
     return H2O_OK;
 }
 
+int h2o_rollout_persistent(h2o_handle h, int n_steps, double dt, double gravity, int trace_every, void* trace_out,
+                           h2o_stream stream)
+{
+    h2o_engine* e = check(h);
+    if (!e) return H2O_ERR_BAD_HANDLE;
+    if (!e->bound) return fail(H2O_ERR_NOT_CONFIGURED, "h2o_bind has not been called");
+    if (e->b_layout != LAYOUT_SPLIT)
+        return fail(H2O_ERR_NOT_CONFIGURED, "persistent rollouts need the split layout (pos, quat, lin_vel, ang_vel)");
+    if (e->param_mode < 0) return fail(H2O_ERR_NOT_CONFIGURED, "no parameters set (h2o_set_params_*)");
+    if (n_steps < 1) return fail(H2O_ERR_BAD_ARGUMENT, "n_steps must be >= 1");
+    if (trace_every < 0 || (trace_every > 0 && !trace_out))
+        return fail(H2O_ERR_BAD_ARGUMENT, "trace_every > 0 needs a trace buffer of (n_steps / trace_every, n_bodies, 9)");
+    if (e->am_dense || e->surface_eta)
+        return fail(H2O_ERR_NOT_CONFIGURED, "persistent rollouts keep the wrapper's added-mass diagonal and a flat surface");
+    if (!(dt > 1e-6)) return H2O_OK;  // hydrodynamics_behavior.py:139
+    DeviceGuard g(e->device);
+    RolloutArgs a;
+    memset(&a, 0, sizeof a);
+    a.pos = const_cast<void*>(e->b_pos); a.quat = const_cast<void*>(e->b_quat);
+    a.lin = const_cast<void*>(e->b_lin); a.ang = const_cast<void*>(e->b_ang);
+    a.prev = e->prev;
+    a.out_force = e->b_f; a.out_torque = e->b_t;
+    a.coeff = e->coeff; a.slot_type = e->slot_type;
+    a.trace = trace_every > 0 ? trace_out : nullptr;
+    a.stats = e->stats_on ? e->stats : nullptr;
+    a.n = e->n;
+    a.n_slots = e->n_slots; a.param_mode = e->param_mode;
+    a.quat_wxyz = e->quat_order == H2O_QUAT_WXYZ;
+    a.n_steps = n_steps; a.trace_every = trace_every;
+    a.dt = dt; a.gravity = gravity; a.rho = e->rho; a.grav = e->grav;
+    for (int k = 0; k < 3; ++k) a.current[k] = e->current[k];
+    a.surface_z = e->surface_z;
+    a.no_fallback = e->no_fallback;
+    // small batches: one warp per CTA so that the warps spread over the SMs (a lone warp per scheduler
+    // issues back to back); large batches: ordinary 128-thread CTAs
+    const int block = e->n <= (long long)e->sm_count * 4 * 32 ? 32 : 128;
+    const int grid = int((e->n + block - 1) / block);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool st = e->stats_on;
+    if (e->dtype == H2O_F32) {
+        if (st) rollout_persistent_kernel<float, true><<<grid, block, 0, s>>>(a);
+        else rollout_persistent_kernel<float, false><<<grid, block, 0, s>>>(a);
+    } else {
+        if (st) rollout_persistent_kernel<double, true><<<grid, block, 0, s>>>(a);
+        else rollout_persistent_kernel<double, false><<<grid, block, 0, s>>>(a);
+    }
+    CUDA_TRY(cudaGetLastError());
+    e->launches += 1;
+    e->last_kernel = H2O_KERNEL_DIRECT;
+    return H2O_OK;
+}
+
 int h2o_components(h2o_handle h, const void* pos, const void* quat, const void* lin_vel, const void* ang_vel,
                    const void* lin_acc, const void* ang_acc, void* const out8[8], void* out_sub_ratio,
                    int32_t* out_flags, h2o_stream stream)

@@ -267,8 +267,54 @@ struct ExactStepOut {
     float ratio;
     int flags;  // bit 0 clamped, bit 1 still
 };
+struct ExactStepConsts {
+    double rho, grav, inv_dt, surface_z;
+    float cx, cy, cz;   // water current as the fast path rounds it
+    int quat_wxyz;
+    const float* am_dense;  // this body's 6x6 matrix or nullptr
+};
+__device__ __noinline__ ExactStepOut body_step_exact_f32(const RawBody<float>& r, const float* c, const ExactStepConsts& k)
+{
+    BodyIn<double, double> g;
+    g.pz = double(r.pz) - k.surface_z;
+    if (k.quat_wxyz) { g.qx = r.q1; g.qy = r.q2; g.qz = r.q3; g.qw = r.q0; }
+    else { g.qx = r.q0; g.qy = r.q1; g.qz = r.q2; g.qw = r.q3; }
+    // flow-relative velocity: the fast path forms it in fp32 (make_body_in), and so does this
+    g.vx = double(r.vx - k.cx); g.vy = double(r.vy - k.cy); g.vz = double(r.vz - k.cz);
+    g.wx = r.wx; g.wy = r.wy; g.wz = r.wz;
+    g.ax = (double(r.vx) - double(r.pvx)) * k.inv_dt; g.ay = (double(r.vy) - double(r.pvy)) * k.inv_dt;
+    g.az = (double(r.vz) - double(r.pvz)) * k.inv_dt;
+    g.bx = (double(r.wx) - double(r.pwx)) * k.inv_dt; g.by = (double(r.wy) - double(r.pwy)) * k.inv_dt;
+    g.bz = (double(r.wz) - double(r.pwz)) * k.inv_dt;
+    g.acc_scale = 1.0;
+    g.dimx = c[0]; g.dimy = c[1]; g.dimz = c[2];
+    g.c_drag = c[3]; g.c_drag_ang = c[4]; g.k_damp = c[5]; g.k_damp_ang = c[6];
+    g.c_am = c[7]; g.c_am_ang = c[8]; g.c_lift = c[9];
+    g.warp_compat = false;
+    g.rho_h = k.rho; g.grav_h = k.grav; g.rho = double(float(k.rho));  // L constants as the fast path rounds them
+    double md[36];
+    g.am_dense = nullptr;
+    if (k.am_dense) {
+        for (int j = 0; j < 36; ++j) md[j] = double(k.am_dense[j]);
+        g.am_dense = md;
+    }
+    Terms<double, double> t;
+    body_terms<double, double, false>(g, t);
+    double F[3], T[3];
+    bool clamped;
+    net_wrench<double, double>(t, double(c[10]), F, T, clamped);
+    ExactStepOut o;
+    for (int j = 0; j < 3; ++j) {
+        o.F[j] = float(F[j]);
+        o.T[j] = float(T[j]);
+    }
+    o.ratio = float(t.ratio);
+    o.flags = (clamped ? 1 : 0) | (t.still ? 2 : 0);
+    return o;
+}
+// Step kernels: re-read the flagged body's inputs from global memory (rare path; the hot path keeps its registers).
 template <int kLayout, int kParam>
-__device__ __noinline__ ExactStepOut body_step_exact_f32(const StepArgs& a, long long i, double surface_z)
+__device__ __noinline__ ExactStepOut body_step_exact_from_global(const StepArgs& a, long long i, double surface_z)
 {
     BodyPtrs<float> bp;
     bp.pos = reinterpret_cast<const float*>(a.pos);
@@ -280,43 +326,15 @@ __device__ __noinline__ ExactStepOut body_step_exact_f32(const StepArgs& a, long
     RawBody<float> r;
     load_raw<float, kLayout>(bp, i, r);
     const float* c = bp.coeff + N_COEFF * (kParam == PARAM_PER_BODY ? i : (long long)a.slot_type[(a.first_body + i) % a.n_slots]);
-    BodyIn<double, double> g;
-    g.pz = double(r.pz) - surface_z;
-    if (a.quat_wxyz) { g.qx = r.q1; g.qy = r.q2; g.qz = r.q3; g.qw = r.q0; }
-    else { g.qx = r.q0; g.qy = r.q1; g.qz = r.q2; g.qw = r.q3; }
-    // flow-relative velocity: the fast path forms it in fp32 (make_body_in), and so does this
-    g.vx = double(r.vx - float(a.current[0])); g.vy = double(r.vy - float(a.current[1])); g.vz = double(r.vz - float(a.current[2]));
-    g.wx = r.wx; g.wy = r.wy; g.wz = r.wz;
-    g.ax = (double(r.vx) - double(r.pvx)) * a.inv_dt; g.ay = (double(r.vy) - double(r.pvy)) * a.inv_dt;
-    g.az = (double(r.vz) - double(r.pvz)) * a.inv_dt;
-    g.bx = (double(r.wx) - double(r.pwx)) * a.inv_dt; g.by = (double(r.wy) - double(r.pwy)) * a.inv_dt;
-    g.bz = (double(r.wz) - double(r.pwz)) * a.inv_dt;
-    g.acc_scale = 1.0;
-    g.dimx = c[0]; g.dimy = c[1]; g.dimz = c[2];
-    g.c_drag = c[3]; g.c_drag_ang = c[4]; g.k_damp = c[5]; g.k_damp_ang = c[6];
-    g.c_am = c[7]; g.c_am_ang = c[8]; g.c_lift = c[9];
-    g.warp_compat = false;
-    g.rho_h = a.rho; g.grav_h = a.grav; g.rho = double(float(a.rho));  // L constants as the fast path rounds them
-    double md[36];
-    g.am_dense = nullptr;
-    if (a.am_dense) {
-        const float* m = reinterpret_cast<const float*>(a.am_dense) + 36 * a.am_slot_type[(a.first_body + i) % a.am_n_slots];
-        for (int k = 0; k < 36; ++k) md[k] = double(m[k]);
-        g.am_dense = md;
-    }
-    Terms<double, double> t;
-    body_terms<double, double, false>(g, t);
-    double F[3], T[3];
-    bool clamped;
-    net_wrench<double, double>(t, double(c[10]), F, T, clamped);
-    ExactStepOut o;
-    for (int k = 0; k < 3; ++k) {
-        o.F[k] = float(F[k]);
-        o.T[k] = float(T[k]);
-    }
-    o.ratio = float(t.ratio);
-    o.flags = (clamped ? 1 : 0) | (t.still ? 2 : 0);
-    return o;
+    float cl[N_COEFF];
+    for (int j = 0; j < N_COEFF; ++j) cl[j] = c[j];
+    ExactStepConsts k;
+    k.rho = a.rho; k.grav = a.grav; k.inv_dt = a.inv_dt; k.surface_z = surface_z;
+    k.cx = float(a.current[0]); k.cy = float(a.current[1]); k.cz = float(a.current[2]);
+    k.quat_wxyz = a.quat_wxyz;
+    k.am_dense = a.am_dense ? reinterpret_cast<const float*>(a.am_dense) + 36 * a.am_slot_type[(a.first_body + i) % a.am_n_slots]
+                            : nullptr;
+    return body_step_exact_f32(r, cl, k);
 }
 
 // fp32 mode: body-frame fast path (returns true when the body must be re-evaluated, see above);
@@ -368,7 +386,7 @@ __device__ __forceinline__ void step_one_body(const StepArgs& a, long long i, co
     if (sizeof(S) == 4) {
         redo = redo && !a.no_fallback;
         if (redo) {
-            const ExactStepOut o = body_step_exact_f32<kLayout, kParam>(a, i, surface_z);
+            const ExactStepOut o = body_step_exact_from_global<kLayout, kParam>(a, i, surface_z);
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 F[k] = S(o.F[k]);
@@ -510,12 +528,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
         fence_proxy_async_smem();
     }
     pdl_wait_prerequisites();  // everything below reads / writes global memory
-    if (kParam == PARAM_TABLE) {
-        const S* g = reinterpret_cast<const S*>(a.coeff);
-        for (int i = tid; i < a.n_types * N_COEFF; i += kThreads) table[i] = g[i];
-        for (int i = tid; i < a.n_slots; i += kThreads) slot_map[i] = static_cast<unsigned char>(a.slot_type[i]);
-    }
-    __syncthreads();
 
     // Tile schedule: full tiles dealt round-robin (tile = cta + it*grid).  At any moment the resident
     // CTAs stream one compact window of every array, which is what DRAM pages and the TLB like.
@@ -544,6 +556,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
         for (int j = 0; j < kStagesIn; ++j)
             if (j < n_it) issue_loads(j, j);
     }
+    // the part-type table is staged AFTER the first tile's bulk loads are in flight: its global-load
+    // latency hides behind theirs (a one-tile-per-CTA launch like C2 is nothing but latencies)
+    if (kParam == PARAM_TABLE) {
+        const S* g = reinterpret_cast<const S*>(a.coeff);
+        for (int i = tid; i < a.n_types * N_COEFF; i += kThreads) table[i] = g[i];
+        for (int i = tid; i < a.n_slots; i += kThreads) slot_map[i] = static_cast<unsigned char>(a.slot_type[i]);
+    }
+    __syncthreads();  // table staged, mbarriers initialised
 
     ThreadStats st;
     const S inv_dt = S(a.inv_dt);
@@ -902,27 +922,21 @@ struct FreeBodyArgs {
     double dt, gravity;            // gravity acts along -z
 };
 
-template <typename S> __global__ void __launch_bounds__(256) free_body_kernel(const __grid_constant__ FreeBodyArgs a)
+// One semi-implicit Euler step of a free box (shared by free_body_kernel and the persistent rollout kernel).
+// State in double, quaternion xyzw; m, dx, dy, dz from the coefficient record.
+struct FreeBodyState {
+    double px, py, pz, qx, qy, qz, qw, vx, vy, vz, wx, wy, wz;
+};
+__device__ __forceinline__ void free_body_update(FreeBodyState& s, double fx, double fy, double fz, double tx, double ty,
+                                                 double tz, double m, double dx, double dy, double dz, double dt,
+                                                 double gravity)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
-    const S* c = reinterpret_cast<const S*>(a.coeff) +
-                 N_COEFF * (a.param_mode == PARAM_PER_BODY ? i : (long long)a.slot_type[i % a.n_slots]);
-    S* P = reinterpret_cast<S*>(a.pos) + 3 * i;
-    S* Q = reinterpret_cast<S*>(a.quat) + 4 * i;
-    S* V = reinterpret_cast<S*>(a.lin) + 3 * i;
-    S* W = reinterpret_cast<S*>(a.ang) + 3 * i;
-    const S* Fp = reinterpret_cast<const S*>(a.force) + 3 * i;
-    const S* Tp = reinterpret_cast<const S*>(a.torque) + 3 * i;
-    const double m = double(c[10]), dx = double(c[0]), dy = double(c[1]), dz = double(c[2]);
-    double qx, qy, qz, qw;
-    if (a.quat_wxyz) { qw = Q[0]; qx = Q[1]; qy = Q[2]; qz = Q[3]; }
-    else { qx = Q[0]; qy = Q[1]; qz = Q[2]; qw = Q[3]; }
-    const double dt = a.dt, im = 1.0 / m;
+    const double qx = s.qx, qy = s.qy, qz = s.qz, qw = s.qw;
+    const double im = 1.0 / m;
     // linear: v += dt (F/m + g)
-    double vx = double(V[0]) + dt * double(Fp[0]) * im;
-    double vy = double(V[1]) + dt * double(Fp[1]) * im;
-    double vz = double(V[2]) + dt * (double(Fp[2]) * im - a.gravity);
+    const double vx = s.vx + dt * fx * im;
+    const double vy = s.vy + dt * fy * im;
+    const double vz = s.vz + dt * (fz * im - gravity);
     // angular, body frame: I w' = tau_b - w_b x (I w_b)
     const double x2 = qx + qx, y2 = qy + qy, z2 = qz + qz;
     const double r00 = 1 - (qy * y2 + qz * z2), r01 = qx * y2 - qw * z2, r02 = qx * z2 + qw * y2;
@@ -930,8 +944,7 @@ template <typename S> __global__ void __launch_bounds__(256) free_body_kernel(co
     const double r20 = qx * z2 - qw * y2, r21 = qy * z2 + qw * x2, r22 = 1 - (qx * x2 + qy * y2);
     const double Ix = m * (dy * dy + dz * dz) / 12.0, Iy = m * (dx * dx + dz * dz) / 12.0,
                  Iz = m * (dx * dx + dy * dy) / 12.0;
-    const double tx = double(Tp[0]), ty = double(Tp[1]), tz = double(Tp[2]);
-    const double wx = double(W[0]), wy = double(W[1]), wz = double(W[2]);
+    const double wx = s.wx, wy = s.wy, wz = s.wz;
     const double tbx = r00 * tx + r10 * ty + r20 * tz, tby = r01 * tx + r11 * ty + r21 * tz,
                  tbz = r02 * tx + r12 * ty + r22 * tz;
     double wbx = r00 * wx + r10 * wy + r20 * wz, wby = r01 * wx + r11 * wy + r21 * wz,
@@ -944,19 +957,165 @@ template <typename S> __global__ void __launch_bounds__(256) free_body_kernel(co
     const double nwx = r00 * wbx + r01 * wby + r02 * wbz, nwy = r10 * wbx + r11 * wby + r12 * wbz,
                  nwz = r20 * wbx + r21 * wby + r22 * wbz;
     // pose with the NEW velocities; q' = q + dt/2 (0,w) * q
-    const double px = double(P[0]) + dt * vx, py = double(P[1]) + dt * vy, pz = double(P[2]) + dt * vz;
+    s.px += dt * vx; s.py += dt * vy; s.pz += dt * vz;
     const double h = 0.5 * dt;
     double nqw = qw - h * (nwx * qx + nwy * qy + nwz * qz);
     double nqx = qx + h * (nwx * qw + nwy * qz - nwz * qy);
     double nqy = qy + h * (nwy * qw + nwz * qx - nwx * qz);
     double nqz = qz + h * (nwz * qw + nwx * qy - nwy * qx);
     const double inv = 1.0 / sqrt(nqx * nqx + nqy * nqy + nqz * nqz + nqw * nqw);
-    nqx *= inv; nqy *= inv; nqz *= inv; nqw *= inv;
-    P[0] = S(px); P[1] = S(py); P[2] = S(pz);
-    V[0] = S(vx); V[1] = S(vy); V[2] = S(vz);
-    W[0] = S(nwx); W[1] = S(nwy); W[2] = S(nwz);
-    if (a.quat_wxyz) { Q[0] = S(nqw); Q[1] = S(nqx); Q[2] = S(nqy); Q[3] = S(nqz); }
-    else { Q[0] = S(nqx); Q[1] = S(nqy); Q[2] = S(nqz); Q[3] = S(nqw); }
+    s.qx = nqx * inv; s.qy = nqy * inv; s.qz = nqz * inv; s.qw = nqw * inv;
+    s.vx = vx; s.vy = vy; s.vz = vz;
+    s.wx = nwx; s.wy = nwy; s.wz = nwz;
+}
+
+template <typename S> __global__ void __launch_bounds__(256) free_body_kernel(const __grid_constant__ FreeBodyArgs a)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const S* c = reinterpret_cast<const S*>(a.coeff) +
+                 N_COEFF * (a.param_mode == PARAM_PER_BODY ? i : (long long)a.slot_type[i % a.n_slots]);
+    S* P = reinterpret_cast<S*>(a.pos) + 3 * i;
+    S* Q = reinterpret_cast<S*>(a.quat) + 4 * i;
+    S* V = reinterpret_cast<S*>(a.lin) + 3 * i;
+    S* W = reinterpret_cast<S*>(a.ang) + 3 * i;
+    const S* Fp = reinterpret_cast<const S*>(a.force) + 3 * i;
+    const S* Tp = reinterpret_cast<const S*>(a.torque) + 3 * i;
+    FreeBodyState s;
+    s.px = P[0]; s.py = P[1]; s.pz = P[2];
+    if (a.quat_wxyz) { s.qw = Q[0]; s.qx = Q[1]; s.qy = Q[2]; s.qz = Q[3]; }
+    else { s.qx = Q[0]; s.qy = Q[1]; s.qz = Q[2]; s.qw = Q[3]; }
+    s.vx = V[0]; s.vy = V[1]; s.vz = V[2];
+    s.wx = W[0]; s.wy = W[1]; s.wz = W[2];
+    free_body_update(s, double(Fp[0]), double(Fp[1]), double(Fp[2]), double(Tp[0]), double(Tp[1]), double(Tp[2]),
+                     double(c[10]), double(c[0]), double(c[1]), double(c[2]), a.dt, a.gravity);
+    P[0] = S(s.px); P[1] = S(s.py); P[2] = S(s.pz);
+    V[0] = S(s.vx); V[1] = S(s.vy); V[2] = S(s.vz);
+    W[0] = S(s.wx); W[1] = S(s.wy); W[2] = S(s.wz);
+    if (a.quat_wxyz) { Q[0] = S(s.qw); Q[1] = S(s.qx); Q[2] = S(s.qy); Q[3] = S(s.qz); }
+    else { Q[0] = S(s.qx); Q[1] = S(s.qy); Q[2] = S(s.qz); Q[3] = S(s.qw); }
+}
+
+// ---------------------------------------------------------------------------
+// rollout_persistent_kernel (BASELINE configs 1 and 5): K steps of
+//   fused force step (hydrodynamics_behavior.py:194-238)  ->  free-body stepper
+// for free bodies in ONE launch.  Bodies are independent, so a thread carries its body's pose,
+// velocities, previous velocities and coefficient record in registers across all K steps: no launch,
+// graph node or global-memory round trip per step.  Every step rounds the state to the storage type
+// exactly where the per-step kernels store it, so the rollout equals K x (step kernel + free_body_kernel)
+// up to FMA contraction.  Every `trace_every` steps (0 = never) a row [p, v, w] per body goes to `trace`
+// (sample-major: (K / trace_every, N, 9)) -- the columns of log_velocity.py:17-20.
+// ---------------------------------------------------------------------------
+struct RolloutArgs {
+    void *pos, *quat, *lin, *ang;  // (N,3) (N,4) (N,3) (N,3) state, updated in place at the end
+    void* prev;                    // (N,6) carried velocities, updated in place at the end
+    void *out_force, *out_torque;  // (N,3) wrench of the LAST step
+    const void* coeff;
+    const int32_t* slot_type;
+    void* trace;                   // optional (samples, N, 9)
+    double* stats;                 // optional statistics over all steps
+    long long n;
+    int n_slots, param_mode, quat_wxyz;
+    int n_steps, trace_every;
+    double dt, gravity, rho, grav;
+    double current[3], surface_z;
+    int no_fallback;
+};
+
+template <typename S, bool kStats>
+__global__ void rollout_persistent_kernel(const __grid_constant__ RolloutArgs a)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    ThreadStats st;
+    if (i < a.n) {
+        const S* c = reinterpret_cast<const S*>(a.coeff) +
+                     N_COEFF * (a.param_mode == PARAM_PER_BODY ? i : (long long)a.slot_type[i % a.n_slots]);
+        S cl[N_COEFF];
+#pragma unroll
+        for (int k = 0; k < N_COEFF; ++k) cl[k] = c[k];
+        S* P = reinterpret_cast<S*>(a.pos) + 3 * i;
+        S* Q = reinterpret_cast<S*>(a.quat) + 4 * i;
+        S* V = reinterpret_cast<S*>(a.lin) + 3 * i;
+        S* W = reinterpret_cast<S*>(a.ang) + 3 * i;
+        S* PV = reinterpret_cast<S*>(a.prev) + 6 * i;
+        RawBody<S> r;
+        r.px = P[0]; r.py = P[1]; r.pz = P[2];
+        r.q0 = Q[0]; r.q1 = Q[1]; r.q2 = Q[2]; r.q3 = Q[3];
+        r.vx = V[0]; r.vy = V[1]; r.vz = V[2];
+        r.wx = W[0]; r.wy = W[1]; r.wz = W[2];
+        r.pvx = PV[0]; r.pvy = PV[1]; r.pvz = PV[2]; r.pwx = PV[3]; r.pwy = PV[4]; r.pwz = PV[5];
+        const Env env{a.current[0], a.current[1], a.current[2], a.surface_z};
+        const S inv_dt = S(1.0 / a.dt);
+        S F[3] = {S(0), S(0), S(0)}, T[3] = {S(0), S(0), S(0)};
+        for (int step = 0; step < a.n_steps; ++step) {
+            BodyIn<double, S> bin;
+            make_body_in<S>(r, cl, a.quat_wxyz, a.rho, a.grav, inv_dt, env, bin);
+            bool clamped, still;
+            double ratio;
+            bool redo = body_step<S>(bin, cl[10], F, T, clamped, still, ratio);
+            if (sizeof(S) == 4) {
+                redo = redo && !a.no_fallback;
+                if (redo) {
+                    RawBody<float> rf;
+                    rf.px = float(r.px); rf.py = float(r.py); rf.pz = float(r.pz);
+                    rf.q0 = float(r.q0); rf.q1 = float(r.q1); rf.q2 = float(r.q2); rf.q3 = float(r.q3);
+                    rf.vx = float(r.vx); rf.vy = float(r.vy); rf.vz = float(r.vz);
+                    rf.wx = float(r.wx); rf.wy = float(r.wy); rf.wz = float(r.wz);
+                    rf.pvx = float(r.pvx); rf.pvy = float(r.pvy); rf.pvz = float(r.pvz);
+                    rf.pwx = float(r.pwx); rf.pwy = float(r.pwy); rf.pwz = float(r.pwz);
+                    float cf[N_COEFF];
+#pragma unroll
+                    for (int k = 0; k < N_COEFF; ++k) cf[k] = float(cl[k]);
+                    ExactStepConsts kc;
+                    kc.rho = a.rho; kc.grav = a.grav; kc.inv_dt = 1.0 / a.dt; kc.surface_z = a.surface_z;
+                    kc.cx = float(a.current[0]); kc.cy = float(a.current[1]); kc.cz = float(a.current[2]);
+                    kc.quat_wxyz = a.quat_wxyz;
+                    kc.am_dense = nullptr;
+                    const ExactStepOut o = body_step_exact_f32(rf, cf, kc);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        F[k] = S(o.F[k]);
+                        T[k] = S(o.T[k]);
+                    }
+                    ratio = double(o.ratio);
+                    clamped = (o.flags & 1) != 0;
+                    still = (o.flags & 2) != 0;
+                }
+            }
+            if (kStats) accumulate_stats(st, double(F[0]), double(F[1]), double(F[2]), ratio, clamped, still, redo);
+            // v_prev <- v (hydrodynamics_behavior.py:237-238), then the stepper
+            r.pvx = r.vx; r.pvy = r.vy; r.pvz = r.vz; r.pwx = r.wx; r.pwy = r.wy; r.pwz = r.wz;
+            FreeBodyState s;
+            s.px = r.px; s.py = r.py; s.pz = r.pz;
+            if (a.quat_wxyz) { s.qw = r.q0; s.qx = r.q1; s.qy = r.q2; s.qz = r.q3; }
+            else { s.qx = r.q0; s.qy = r.q1; s.qz = r.q2; s.qw = r.q3; }
+            s.vx = r.vx; s.vy = r.vy; s.vz = r.vz;
+            s.wx = r.wx; s.wy = r.wy; s.wz = r.wz;
+            free_body_update(s, double(F[0]), double(F[1]), double(F[2]), double(T[0]), double(T[1]), double(T[2]),
+                             double(cl[10]), double(cl[0]), double(cl[1]), double(cl[2]), a.dt, a.gravity);
+            r.px = S(s.px); r.py = S(s.py); r.pz = S(s.pz);
+            r.vx = S(s.vx); r.vy = S(s.vy); r.vz = S(s.vz);
+            r.wx = S(s.wx); r.wy = S(s.wy); r.wz = S(s.wz);
+            if (a.quat_wxyz) { r.q0 = S(s.qw); r.q1 = S(s.qx); r.q2 = S(s.qy); r.q3 = S(s.qz); }
+            else { r.q0 = S(s.qx); r.q1 = S(s.qy); r.q2 = S(s.qz); r.q3 = S(s.qw); }
+            if (a.trace && a.trace_every > 0 && (step + 1) % a.trace_every == 0) {
+                S* tr = reinterpret_cast<S*>(a.trace) + ((long long)((step + 1) / a.trace_every - 1) * a.n + i) * 9;
+                tr[0] = r.px; tr[1] = r.py; tr[2] = r.pz;
+                tr[3] = r.vx; tr[4] = r.vy; tr[5] = r.vz;
+                tr[6] = r.wx; tr[7] = r.wy; tr[8] = r.wz;
+            }
+        }
+        P[0] = r.px; P[1] = r.py; P[2] = r.pz;
+        Q[0] = r.q0; Q[1] = r.q1; Q[2] = r.q2; Q[3] = r.q3;
+        V[0] = r.vx; V[1] = r.vy; V[2] = r.vz;
+        W[0] = r.wx; W[1] = r.wy; W[2] = r.wz;
+        PV[0] = r.pvx; PV[1] = r.pvy; PV[2] = r.pvz; PV[3] = r.pwx; PV[4] = r.pwy; PV[5] = r.pwz;
+        S* of = reinterpret_cast<S*>(a.out_force) + 3 * i;
+        S* ot = reinterpret_cast<S*>(a.out_torque) + 3 * i;
+        of[0] = F[0]; of[1] = F[1]; of[2] = F[2];
+        ot[0] = T[0]; ot[1] = T[1]; ot[2] = T[2];
+    }
+    if (kStats && a.stats) flush_stats(st, a.stats);
 }
 
 }  // namespace h2o

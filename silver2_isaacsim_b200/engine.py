@@ -374,6 +374,18 @@ class HydroEngine:
     def launch_rollout(self):
         L.check(self._lib.h2o_launch_rollout(self._h, _stream_ptr(self.device)))
 
+    def rollout_persistent(self, n_steps: int, dt: float, gravity: float = 9.81, trace_every: int = 0):
+        """``n_steps`` x (fused force step -> free-body stepper) over the bound split-layout tensors in ONE
+        kernel launch (state in registers across the steps).  Returns the trace tensor
+        ``(n_steps // trace_every, n_bodies, 9)`` = [p, v, w] rows when ``trace_every > 0``, else ``None``."""
+        trace = None
+        if trace_every > 0:
+            trace = self._empty(max(1, n_steps // trace_every), self.n_bodies, 9)
+        L.check(self._lib.h2o_rollout_persistent(self._h, int(n_steps), float(dt), float(gravity), int(trace_every),
+                                                 ctypes.c_void_p(trace.data_ptr()) if trace is not None else None,
+                                                 _stream_ptr(self.device)))
+        return trace
+
     # ------------------------------------------------------------------ components
     def components(self, position, orientation_quat, linear_vel, angular_vel, linear_accel, angular_accel,
                    return_flags: bool = False):

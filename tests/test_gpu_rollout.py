@@ -107,6 +107,71 @@ def test_c1_free_running_graph_rollout(buoy_record, dev):
     assert abs(pos.cpu().numpy()[0][2] - pf[2]) < 5e-3 and abs(pf[2]) < 5e-3  # same waterline
 
 
+def test_c1_persistent_rollout_kernel(buoy_record, dev):
+    """The same 10 000 free-running steps in ONE kernel launch (state in registers across the steps),
+    validated exactly like the graph rollout above, plus the trace the kernel writes every 100 steps."""
+    from silver2_isaacsim_b200 import HydroEngine
+
+    wl, ctor, mass, rec = buoy_record
+    e = HydroEngine(1, dtype=torch.float64, device=dev)
+    e.set_params_uniform(ctor, mass)
+    t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64), device=dev).contiguous()
+    pos, quat, v, w = t(wl.pos), t(wl.quat_xyzw), t(wl.lin_vel), t(wl.ang_vel)
+    F, T = e.bind(pos, quat, v, w)
+    trace = e.rollout_persistent(10000, wl.dt, gravity=wl.g, trace_every=100)
+    torch.cuda.synchronize()
+    assert e.launch_count == 1 and tuple(trace.shape) == (100, 1, 9)
+    tr = trace.cpu().numpy()[:, 0]
+    drift = {n: float(np.abs(tr[n // 100 - 1, :3] - rec["pos"][n]).max()) for n in (100, 200, 500, 1000, 5000)}
+    pf, qf, vf, wf = rec["final"]
+    drift[10000] = float(np.abs(pos.cpu().numpy()[0] - pf).max())
+    print("persistent rollout drift |p_gpu - p_numpy|:", {k: "%.2e" % d for k, d in drift.items()})
+    assert drift[100] < 1e-11 and drift[200] < 1e-9, drift
+    assert max(drift.values()) < 2e-2, drift
+    assert np.abs(v.cpu().numpy()[0] - vf).max() < 2e-2
+    assert abs(pos.cpu().numpy()[0][2] - pf[2]) < 5e-3 and abs(pf[2]) < 5e-3  # same waterline
+    assert np.array_equal(tr[-1, :3], pos.cpu().numpy()[0]) and np.array_equal(tr[-1, 3:6], v.cpu().numpy()[0])
+    # carried velocities = the velocities before the last stepper call; last wrench in the bound outputs
+    assert torch.isfinite(F).all() and torch.isfinite(T).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["fp32", "fp64"])
+@pytest.mark.parametrize("params", ["table", "per_body"])
+def test_persistent_rollout_equals_stepwise(dev, dtype, params):
+    """C5-style batch: K steps in one persistent launch == K x (fused step + free-body stepper) launched
+    one by one (same arithmetic, same roundings of the carried state; only FMA contraction may differ)."""
+    wl = W.uniform_small_batch(1024) if params == "table" else W.heterogeneous_boxes(3000, seed=88, xy_range=2.0)
+    K = 25
+    res = []
+    for mode in ("stepwise", "persistent"):
+        from silver2_isaacsim_b200 import HydroEngine
+        e = HydroEngine(wl.n, dtype=dtype, device=dev)
+        e.set_workload_params(wl)
+        e.enable_stats(True)
+        tt = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev).to(dtype).contiguous()
+        ten = [tt(a) for a in (wl.pos, wl.quat_xyzw, wl.lin_vel, wl.ang_vel)]
+        e.set_prev(tt(wl.prev_lin), tt(wl.prev_ang))
+        F, T = e.bind(*ten)
+        if mode == "stepwise":
+            for _ in range(K):
+                e.step_bound(wl.dt)
+                e.integrate_free_bodies(*ten, F, T, wl.dt, wl.g)
+        else:
+            e.rollout_persistent(K, wl.dt, gravity=wl.g)
+        torch.cuda.synchronize()
+        st = e.stats(reset=True)
+        assert st["bodies"] == K * wl.n and st["nonfinite_bodies"] == 0
+        res.append([x.double().cpu().numpy() for x in ten] + [F.double().cpu().numpy(), T.double().cpu().numpy(),
+                                                              e.prev_velocities().double().cpu().numpy()])
+        assert e.launch_count == (2 * K if mode == "stepwise" else 1)
+    tol = 2e-4 if dtype == torch.float32 else 1e-9   # 25 steps of a discontinuous model amplify rounding
+    names = ("pos", "quat", "lin_vel", "ang_vel", "force", "torque", "prev")
+    for name, a, b in zip(names, *res):
+        scale = np.abs(a).max(axis=1, keepdims=True) + 1e-3
+        frac = float((np.abs(a - b) <= tol * scale).all(axis=1).mean())
+        assert frac >= 0.995, (name, frac)   # the rest: a keypoint crossed the surface one step apart
+
+
 class FakeRigidPrimView:
     """Stand-in for omni.isaac.core.prims.RigidPrimView (the three methods the reference uses)."""
 
