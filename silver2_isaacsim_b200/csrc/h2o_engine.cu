@@ -504,7 +504,7 @@ int h2o_create(h2o_handle* out, int64_t n_bodies, int dtype, int device)
     e->sm_count = prop.multiProcessorCount;
     if (const char* v = getenv("H2O_MAX_CTAS_PER_SM")) e->max_ctas_per_sm = atoi(v);
     if (const char* v = getenv("H2O_PDL")) e->use_pdl = atoi(v) != 0;
-    if (const char* v = getenv("H2O_NO_FALLBACK")) e->no_fallback = atoi(v) != 0;
+    if (const char* v = getenv("H2O_NO_FALLBACK")) e->no_fallback = std::max(0, atoi(v));
     if (const char* v = getenv("H2O_ROBOT_CFG")) e->robot_cfg = std::max(-1, std::min(2, atoi(v)));
     if (cudaMalloc(&e->prev, size_t(n_bodies) * 6 * e->esz) != cudaSuccess ||
         cudaMalloc(reinterpret_cast<void**>(&e->stats), N_STATS * sizeof(double)) != cudaSuccess ||

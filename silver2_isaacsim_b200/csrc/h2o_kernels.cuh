@@ -78,7 +78,8 @@ struct StepArgs {
     // nullptr = equal runs of bodies_per_robot.  Wrenches then come from robot_wrench_kernel.
     const long long* robot_offsets;
     long long n_robots_var;
-    int no_fallback;         // study knob (H2O_NO_FALLBACK=1): keep the fast-path result of flagged bodies
+    int no_fallback;         // study knob H2O_NO_FALLBACK: 1 = keep the fast-path result of flagged bodies,
+                             // k > 1 = re-evaluate exactly every k-th body instead (cost measurements)
 };
 
 // ---------------------------------------------------------------------------
@@ -147,6 +148,10 @@ template <int N> __device__ __forceinline__ void bulk_wait_all()
 // this one drains, and make this one wait for its predecessor before touching global memory.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait_prerequisites() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2_keep(const void* p)
+{
+    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -174,7 +179,7 @@ template <typename S> struct RawBody {
     S pvx, pvy, pvz, pwx, pwy, pwz;
 };
 
-template <typename S, int kLayout>
+template <typename S, int kLayout, bool kPrevRow = false>
 __device__ __forceinline__ void load_raw(const BodyPtrs<S>& p, long long i, RawBody<S>& r)
 {
     using V2 = typename Vec2Of<S>::type;
@@ -207,7 +212,8 @@ __device__ __forceinline__ void load_raw(const BodyPtrs<S>& p, long long i, RawB
         const V2 a = pv[0], b = pv[1], c = pv[2];
         r.vx = a.x; r.vy = a.y; r.vz = b.x; r.wx = b.y; r.wy = c.x; r.wz = c.y;
     }
-    const V2* pr = reinterpret_cast<const V2*>(p.prev + 6 * i);
+    // kPrevRow: p.prev already points at this body's six previous velocities (a saved copy)
+    const V2* pr = reinterpret_cast<const V2*>(kPrevRow ? p.prev : p.prev + 6 * i);
     const V2 a = pr[0], b = pr[1], c = pr[2];
     r.pvx = a.x; r.pvy = a.y; r.pvz = b.x; r.pwx = b.y; r.pwy = c.x; r.pwz = c.y;
 }
@@ -267,35 +273,32 @@ struct ExactStepOut {
     float ratio;
     int flags;  // bit 0 clamped, bit 1 still
 };
-struct ExactStepConsts {
-    double rho, grav, inv_dt, surface_z;
-    float cx, cy, cz;   // water current as the fast path rounds it
-    int quat_wxyz;
-    const float* am_dense;  // this body's 6x6 matrix or nullptr
-};
-__device__ __noinline__ ExactStepOut body_step_exact_f32(const RawBody<float>& r, const float* c, const ExactStepConsts& k)
+// Core (inlined into its two noinline carriers below): the fp64-mode arithmetic on one fp32-stored body.
+__device__ __forceinline__ ExactStepOut exact_eval_f32(const RawBody<float>& r, const float* c, int quat_wxyz, double rho,
+                                                        double grav, double inv_dt, double surface_z, float cx, float cy,
+                                                        float cz, const float* am_dense)
 {
     BodyIn<double, double> g;
-    g.pz = double(r.pz) - k.surface_z;
-    if (k.quat_wxyz) { g.qx = r.q1; g.qy = r.q2; g.qz = r.q3; g.qw = r.q0; }
+    g.pz = double(r.pz) - surface_z;
+    if (quat_wxyz) { g.qx = r.q1; g.qy = r.q2; g.qz = r.q3; g.qw = r.q0; }
     else { g.qx = r.q0; g.qy = r.q1; g.qz = r.q2; g.qw = r.q3; }
     // flow-relative velocity: the fast path forms it in fp32 (make_body_in), and so does this
-    g.vx = double(r.vx - k.cx); g.vy = double(r.vy - k.cy); g.vz = double(r.vz - k.cz);
+    g.vx = double(r.vx - cx); g.vy = double(r.vy - cy); g.vz = double(r.vz - cz);
     g.wx = r.wx; g.wy = r.wy; g.wz = r.wz;
-    g.ax = (double(r.vx) - double(r.pvx)) * k.inv_dt; g.ay = (double(r.vy) - double(r.pvy)) * k.inv_dt;
-    g.az = (double(r.vz) - double(r.pvz)) * k.inv_dt;
-    g.bx = (double(r.wx) - double(r.pwx)) * k.inv_dt; g.by = (double(r.wy) - double(r.pwy)) * k.inv_dt;
-    g.bz = (double(r.wz) - double(r.pwz)) * k.inv_dt;
+    g.ax = (double(r.vx) - double(r.pvx)) * inv_dt; g.ay = (double(r.vy) - double(r.pvy)) * inv_dt;
+    g.az = (double(r.vz) - double(r.pvz)) * inv_dt;
+    g.bx = (double(r.wx) - double(r.pwx)) * inv_dt; g.by = (double(r.wy) - double(r.pwy)) * inv_dt;
+    g.bz = (double(r.wz) - double(r.pwz)) * inv_dt;
     g.acc_scale = 1.0;
     g.dimx = c[0]; g.dimy = c[1]; g.dimz = c[2];
     g.c_drag = c[3]; g.c_drag_ang = c[4]; g.k_damp = c[5]; g.k_damp_ang = c[6];
     g.c_am = c[7]; g.c_am_ang = c[8]; g.c_lift = c[9];
     g.warp_compat = false;
-    g.rho_h = k.rho; g.grav_h = k.grav; g.rho = double(float(k.rho));  // L constants as the fast path rounds them
+    g.rho_h = rho; g.grav_h = grav; g.rho = double(float(rho));  // L constants as the fast path rounds them
     double md[36];
     g.am_dense = nullptr;
-    if (k.am_dense) {
-        for (int j = 0; j < 36; ++j) md[j] = double(k.am_dense[j]);
+    if (am_dense) {
+        for (int j = 0; j < 36; ++j) md[j] = double(am_dense[j]);
         g.am_dense = md;
     }
     Terms<double, double> t;
@@ -304,6 +307,7 @@ __device__ __noinline__ ExactStepOut body_step_exact_f32(const RawBody<float>& r
     bool clamped;
     net_wrench<double, double>(t, double(c[10]), F, T, clamped);
     ExactStepOut o;
+#pragma unroll
     for (int j = 0; j < 3; ++j) {
         o.F[j] = float(F[j]);
         o.T[j] = float(T[j]);
@@ -312,29 +316,144 @@ __device__ __noinline__ ExactStepOut body_step_exact_f32(const RawBody<float>& r
     o.flags = (clamped ? 1 : 0) | (t.still ? 2 : 0);
     return o;
 }
-// Step kernels: re-read the flagged body's inputs from global memory (rare path; the hot path keeps its registers).
-template <int kLayout, int kParam>
-__device__ __noinline__ ExactStepOut body_step_exact_from_global(const StepArgs& a, long long i, double surface_z)
+// Persistent rollout kernel: the body's state lives in registers; handed over by reference (rare path).
+__device__ __noinline__ ExactStepOut body_step_exact_f32(const RawBody<float>& r, const float* c, int quat_wxyz, double rho,
+                                                         double grav, double inv_dt, double surface_z, float cx, float cy,
+                                                         float cz)
+{
+    return exact_eval_f32(r, c, quat_wxyz, rho, grav, inv_dt, surface_z, cx, cy, cz, nullptr);
+}
+// Step kernels: re-read the flagged body's inputs from global memory (they are L2-resident: the tile was
+// streamed in microseconds ago), so the hot path keeps no input alive for this.  Scalars cross the call by
+// value (registers), nothing goes through local memory.
+template <int kLayout, int kParam, bool kPrevRow>
+__device__ __noinline__ ExactStepOut body_step_exact_from_global(
+    const float* pos, const float* quat, const float* lin, const float* ang, const float* prev, const float* coeff,
+    const int32_t* slot_type, long long i, long long first_body, int n_slots, int quat_wxyz, double rho, double grav,
+    double inv_dt, double surface_z, float cx, float cy, float cz, const float* am_dense)
 {
     BodyPtrs<float> bp;
-    bp.pos = reinterpret_cast<const float*>(a.pos);
-    bp.quat = reinterpret_cast<const float*>(a.quat);
-    bp.lin = reinterpret_cast<const float*>(a.lin);
-    bp.ang = reinterpret_cast<const float*>(a.ang);
-    bp.prev = reinterpret_cast<const float*>(a.prev);
-    bp.coeff = reinterpret_cast<const float*>(a.coeff);
+    bp.pos = pos; bp.quat = quat; bp.lin = lin; bp.ang = ang; bp.prev = prev; bp.coeff = coeff;
     RawBody<float> r;
-    load_raw<float, kLayout>(bp, i, r);
-    const float* c = bp.coeff + N_COEFF * (kParam == PARAM_PER_BODY ? i : (long long)a.slot_type[(a.first_body + i) % a.n_slots]);
+    load_raw<float, kLayout, kPrevRow>(bp, i, r);
+    const float* c = coeff + N_COEFF * (kParam == PARAM_PER_BODY ? i : (long long)slot_type[(first_body + i) % n_slots]);
     float cl[N_COEFF];
+#pragma unroll
     for (int j = 0; j < N_COEFF; ++j) cl[j] = c[j];
-    ExactStepConsts k;
-    k.rho = a.rho; k.grav = a.grav; k.inv_dt = a.inv_dt; k.surface_z = surface_z;
-    k.cx = float(a.current[0]); k.cy = float(a.current[1]); k.cz = float(a.current[2]);
-    k.quat_wxyz = a.quat_wxyz;
-    k.am_dense = a.am_dense ? reinterpret_cast<const float*>(a.am_dense) + 36 * a.am_slot_type[(a.first_body + i) % a.am_n_slots]
-                            : nullptr;
-    return body_step_exact_f32(r, cl, k);
+    return exact_eval_f32(r, cl, quat_wxyz, rho, grav, inv_dt, surface_z, cx, cy, cz, am_dense);
+}
+// prev_row: nullptr = the body's row of a.prev (still the OLD velocities), else a saved copy of that row
+template <int kLayout, int kParam>
+__device__ __forceinline__ ExactStepOut redo_exact(const StepArgs& a, long long i, double surface_z,
+                                                   const float* prev_row = nullptr)
+{
+    const float* am = a.am_dense ? reinterpret_cast<const float*>(a.am_dense) + 36 * a.am_slot_type[(a.first_body + i) % a.am_n_slots]
+                                 : nullptr;
+    if (prev_row)
+        return body_step_exact_from_global<kLayout, kParam, true>(
+            reinterpret_cast<const float*>(a.pos), reinterpret_cast<const float*>(a.quat),
+            reinterpret_cast<const float*>(a.lin), reinterpret_cast<const float*>(a.ang), prev_row,
+            reinterpret_cast<const float*>(a.coeff), a.slot_type, i, a.first_body, a.n_slots, a.quat_wxyz, a.rho, a.grav,
+            a.inv_dt, surface_z, float(a.current[0]), float(a.current[1]), float(a.current[2]), am);
+    return body_step_exact_from_global<kLayout, kParam, false>(
+        reinterpret_cast<const float*>(a.pos), reinterpret_cast<const float*>(a.quat), reinterpret_cast<const float*>(a.lin),
+        reinterpret_cast<const float*>(a.ang), reinterpret_cast<const float*>(a.prev), reinterpret_cast<const float*>(a.coeff),
+        a.slot_type, i, a.first_body, a.n_slots, a.quat_wxyz, a.rho, a.grav, a.inv_dt, surface_z, float(a.current[0]),
+        float(a.current[1]), float(a.current[2]), am);
+}
+
+// Deferred re-evaluation at the end of a tile-kernel CTA: one saved body per lane, and the float64 model split
+// into four ROLES that four warps evaluate concurrently (a single lane doing all of it under the step
+// kernel's register cap takes ~4 us, which is pure tail latency; profiles/r02_fallback_cost.md).  Every role
+// instantiates the same body_terms; the compiler keeps only the chains its outputs need.
+enum : int { ROLE_DRAG = 0, ROLE_LIFT = 1, ROLE_HYDROSTATIC = 2, ROLE_ADDED_MASS = 3, N_ROLES = 4, ROLE_DOUBLES = 10 };
+template <int kRole, int kLayout, int kParam>
+__device__ __noinline__ void exact_role_from_global(
+    const float* pos, const float* quat, const float* lin, const float* ang, const float* prev_row, const float* coeff,
+    const int32_t* slot_type, long long i, long long first_body, int n_slots, int quat_wxyz, double rho, double grav,
+    double inv_dt, double surface_z, float cx, float cy, float cz, double* out)
+{
+    BodyPtrs<float> bp;
+    bp.pos = pos; bp.quat = quat; bp.lin = lin; bp.ang = ang; bp.prev = prev_row; bp.coeff = coeff;
+    RawBody<float> r;
+    load_raw<float, kLayout, true>(bp, i, r);
+    const float* c = coeff + N_COEFF * (kParam == PARAM_PER_BODY ? i : (long long)slot_type[(first_body + i) % n_slots]);
+    BodyIn<double, double> g;
+    g.pz = double(r.pz) - surface_z;
+    if (quat_wxyz) { g.qx = r.q1; g.qy = r.q2; g.qz = r.q3; g.qw = r.q0; }
+    else { g.qx = r.q0; g.qy = r.q1; g.qz = r.q2; g.qw = r.q3; }
+    g.vx = double(r.vx - cx); g.vy = double(r.vy - cy); g.vz = double(r.vz - cz);
+    g.wx = r.wx; g.wy = r.wy; g.wz = r.wz;
+    g.ax = (double(r.vx) - double(r.pvx)) * inv_dt; g.ay = (double(r.vy) - double(r.pvy)) * inv_dt;
+    g.az = (double(r.vz) - double(r.pvz)) * inv_dt;
+    g.bx = (double(r.wx) - double(r.pwx)) * inv_dt; g.by = (double(r.wy) - double(r.pwy)) * inv_dt;
+    g.bz = (double(r.wz) - double(r.pwz)) * inv_dt;
+    g.acc_scale = 1.0;
+    g.dimx = c[0]; g.dimy = c[1]; g.dimz = c[2];
+    g.c_drag = c[3]; g.c_drag_ang = c[4]; g.k_damp = c[5]; g.k_damp_ang = c[6];
+    g.c_am = c[7]; g.c_am_ang = c[8]; g.c_lift = c[9];
+    g.warp_compat = false;
+    g.rho_h = rho; g.grav_h = grav; g.rho = double(float(rho));
+    g.am_dense = nullptr;
+    Terms<double, double> t;
+    body_terms<double, double, false>(g, t);
+    if (kRole == ROLE_DRAG) {
+        out[0] = t.fd[0]; out[1] = t.fd[1]; out[2] = t.fd[2];
+        out[3] = t.tarm[0]; out[4] = t.tarm[1]; out[5] = t.tarm[2];
+        out[6] = t.cop[0]; out[7] = t.cop[1]; out[8] = t.cop[2];
+    } else if (kRole == ROLE_LIFT) {
+        out[0] = t.fl[0]; out[1] = t.fl[1]; out[2] = t.fl[2];
+    } else if (kRole == ROLE_HYDROSTATIC) {
+        out[0] = t.td[0]; out[1] = t.td[1]; out[2] = t.td[2];
+        out[3] = t.cob[0]; out[4] = t.cob[1]; out[5] = t.cob[2];
+        out[6] = t.fbz; out[7] = double(c[10]);
+    } else {
+        out[0] = t.fam[0]; out[1] = t.fam[1]; out[2] = t.fam[2];
+        out[3] = t.tam[0]; out[4] = t.tam[1]; out[5] = t.tam[2];
+    }
+}
+template <int kLayout, int kParam>
+__device__ __forceinline__ void redo_role(int role, const StepArgs& a, long long i, double surface_z, const float* prev_row,
+                                          double* out)
+{
+#define H2O_ROLE(R)                                                                                                        \
+    exact_role_from_global<R, kLayout, kParam>(                                                                            \
+        reinterpret_cast<const float*>(a.pos), reinterpret_cast<const float*>(a.quat), reinterpret_cast<const float*>(a.lin), \
+        reinterpret_cast<const float*>(a.ang), prev_row, reinterpret_cast<const float*>(a.coeff), a.slot_type, i,         \
+        a.first_body, a.n_slots, a.quat_wxyz, a.rho, a.grav, a.inv_dt, surface_z, float(a.current[0]), float(a.current[1]), \
+        float(a.current[2]), out)
+    if (role == ROLE_DRAG) H2O_ROLE(ROLE_DRAG);
+    else if (role == ROLE_LIFT) H2O_ROLE(ROLE_LIFT);
+    else if (role == ROLE_HYDROSTATIC) H2O_ROLE(ROLE_HYDROSTATIC);
+    else H2O_ROLE(ROLE_ADDED_MASS);
+#undef H2O_ROLE
+}
+// the four partial results of one body -> net wrench + clamp (hydrodynamics_behavior.py:212-226)
+__device__ __noinline__ ExactStepOut combine_roles(const double* p)
+{
+    Terms<double, double> t;
+    const double* d = p + ROLE_DRAG * ROLE_DOUBLES;
+    const double* l = p + ROLE_LIFT * ROLE_DOUBLES;
+    const double* h = p + ROLE_HYDROSTATIC * ROLE_DOUBLES;
+    const double* m = p + ROLE_ADDED_MASS * ROLE_DOUBLES;
+    for (int k = 0; k < 3; ++k) {
+        t.fd[k] = d[k]; t.tarm[k] = d[3 + k]; t.cop[k] = d[6 + k];
+        t.fl[k] = l[k];
+        t.td[k] = h[k]; t.cob[k] = h[3 + k];
+        t.fam[k] = m[k]; t.tam[k] = m[3 + k];
+    }
+    t.fbz = h[6];
+    double F[3], T[3];
+    bool clamped;
+    net_wrench<double, double>(t, h[7], F, T, clamped);
+    ExactStepOut o;
+    for (int k = 0; k < 3; ++k) {
+        o.F[k] = float(F[k]);
+        o.T[k] = float(T[k]);
+    }
+    o.ratio = 0.f;
+    o.flags = clamped ? 1 : 0;
+    return o;
 }
 
 // fp32 mode: body-frame fast path (returns true when the body must be re-evaluated, see above);
@@ -374,19 +493,21 @@ __device__ __forceinline__ void accumulate_stats(ThreadStats& st, double fx, dou
     st.redone += redone ? 1u : 0u;
 }
 
-// One body of a step kernel: fast path, float64 re-evaluation when flagged (fp32 mode), statistics.
+// One body of a step kernel: fast path + statistics.  Returns true when the body is flagged for the float64
+// re-evaluation; kDefer = false does it on the spot (redo_exact), kDefer = true leaves it to the caller.
 // `i` = body index inside the launch (a.pos etc. are the launch's base pointers).
-template <typename S, int kLayout, int kParam, bool kStats>
-__device__ __forceinline__ void step_one_body(const StepArgs& a, long long i, const BodyIn<double, S>& in, S mass,
+template <typename S, int kLayout, int kParam, bool kStats, bool kDefer>
+__device__ __forceinline__ bool step_one_body(const StepArgs& a, long long i, const BodyIn<double, S>& in, S mass,
                                               double surface_z, S F[3], S T[3], ThreadStats& st)
 {
     bool clamped, still;
     double ratio;
     bool redo = body_step<S>(in, mass, F, T, clamped, still, ratio);
     if (sizeof(S) == 4) {
-        redo = redo && !a.no_fallback;
-        if (redo) {
-            const ExactStepOut o = body_step_exact_from_global<kLayout, kParam>(a, i, surface_z);
+        redo = redo && a.no_fallback != 1;
+        if (a.no_fallback > 1) redo = ((a.first_body + i) % a.no_fallback) == 0;  // study knob: every k-th body
+        if (redo && !kDefer) {
+            const ExactStepOut o = redo_exact<kLayout, kParam>(a, i, surface_z);
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 F[k] = S(o.F[k]);
@@ -398,6 +519,7 @@ __device__ __forceinline__ void step_one_body(const StepArgs& a, long long i, co
         }
     }
     if (kStats) accumulate_stats(st, double(F[0]), double(F[1]), double(F[2]), ratio, clamped, still, redo);
+    return redo;
 }
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -451,6 +573,17 @@ template <typename S, int kLayout, int kParam> struct TileLayout {
     static constexpr int E_OUT = 3 + 3 + 6;  // force, torque, prev
 };
 
+// Bodies the fp32 fast path flags are not re-evaluated on the spot (one lane working for microseconds would
+// stall its whole CTA at the next barrier, tile after tile): the lane saves the body index and its OLD
+// previous velocities (the tile's bulk store is about to overwrite them) and the CTA re-evaluates all its
+// saved bodies at the very end, one per lane in parallel, while its last bulk stores drain, then patches
+// force / torque (/ robot wrench) with plain stores.  Measured: profiles/r02_fallback_cost.md.
+struct RedoEntry {
+    long long body;   // index inside the launch
+    float prev[6];    // previous [v, w] as they were before this step
+};
+constexpr int REDO_CAP = 24;  // 24 bodies x 4 roles x 10 doubles of scratch fit the smallest input stage
+
 template <typename S, int kLayout, int kParam, int kThreads, int kStagesIn, int kStagesOut>
 struct TileSmem {
     using TL = TileLayout<S, kLayout, kParam>;
@@ -460,11 +593,12 @@ struct TileSmem {
         (kParam == PARAM_TABLE) ? (size_t(MAX_TABLE_TYPES) * N_COEFF * sizeof(S) + MAX_TABLE_SLOTS) : 0;
     static constexpr size_t ROBOT_BYTES = size_t(kThreads) * 6 * sizeof(S);  // [3][tile] transferred torques + [3][tile] arms
     static constexpr size_t BAR_BYTES = 16 * sizeof(uint64_t);
+    static constexpr size_t REDO_BYTES = 16 + size_t(REDO_CAP) * sizeof(RedoEntry);  // count + deferred re-evaluations
     static constexpr size_t OFF_IN = 0;
     static constexpr size_t OFF_OUT = OFF_IN + kStagesIn * IN_BYTES;
     static constexpr size_t OFF_TABLE = OFF_OUT + kStagesOut * OUT_BYTES;
     static constexpr size_t OFF_ROBOT = (OFF_TABLE + TABLE_BYTES + 15) / 16 * 16;
-    static constexpr size_t total(bool robots) { return OFF_ROBOT + (robots ? ROBOT_BYTES : 0) + BAR_BYTES; }
+    static constexpr size_t total(bool robots) { return OFF_ROBOT + (robots ? ROBOT_BYTES : 0) + BAR_BYTES + REDO_BYTES; }
 };
 
 // ---------------------------------------------------------------------------
@@ -509,6 +643,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
     S* const robot_acc = reinterpret_cast<S*>(smem + SM::OFF_ROBOT);
     uint64_t* const full_bar =
         reinterpret_cast<uint64_t*>(smem + SM::OFF_ROBOT + (kRobot ? SM::ROBOT_BYTES : 0));
+    int* const redo_count = reinterpret_cast<int*>(smem + SM::OFF_ROBOT + (kRobot ? SM::ROBOT_BYTES : 0) + SM::BAR_BYTES);
+    RedoEntry* const redo_list = reinterpret_cast<RedoEntry*>(reinterpret_cast<unsigned char*>(redo_count) + 16);
 
     // per-stream byte sizes of one full tile and offsets inside a stage
     const uint32_t b_pos = uint32_t(TL::E_POS) * TB * sizeof(S);
@@ -526,6 +662,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
         for (int s = 0; s < kStagesIn; ++s) mbar_init(&full_bar[s], 1);
         mbar_fence_init();
         fence_proxy_async_smem();
+        *redo_count = 0;
     }
     pdl_wait_prerequisites();  // everything below reads / writes global memory
 
@@ -632,7 +769,34 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
             } else {
                 BodyIn<double, S> bin;
                 make_body_in<S>(r, cl, a.quat_wxyz, a.rho, a.grav, inv_dt, env, bin);
-                step_one_body<S, kLayout, kParam, kStats>(a, tile_begin + tid, bin, cl[10], env.surface_z, F, T, st);
+                if (step_one_body<S, kLayout, kParam, kStats, true>(a, tile_begin + tid, bin, cl[10], env.surface_z, F, T, st)) {
+                    if (sizeof(S) == 4) {
+                        const long long bi = tile_begin + tid;
+                        const int slot = atomicAdd(redo_count, 1);
+                        if (slot < REDO_CAP) {  // prev[bi] in global memory is still the old row: this tile's store comes later
+                            const float2* pr = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(a.prev) + 6 * bi);
+                            const float2 p0 = pr[0], p1 = pr[1], p2 = pr[2];
+                            // keep the body's rows L2-resident until the CTA gets to it (the batch is larger
+                            // than the L2: by then they would come from HBM again, ~1 us of the tail)
+                            prefetch_l2_keep(reinterpret_cast<const S*>(a.pos) + TL::E_POS * bi);
+                            if (TL::E_QUAT) prefetch_l2_keep(reinterpret_cast<const S*>(a.quat) + TL::E_QUAT * bi);
+                            prefetch_l2_keep(reinterpret_cast<const S*>(a.lin) + TL::E_LIN * bi);
+                            if (TL::E_ANG) prefetch_l2_keep(reinterpret_cast<const S*>(a.ang) + TL::E_ANG * bi);
+                            if (TL::E_COEFF) prefetch_l2_keep(reinterpret_cast<const S*>(a.coeff) + TL::E_COEFF * bi);
+                            RedoEntry& en = redo_list[slot];
+                            en.body = bi;
+                            en.prev[0] = p0.x; en.prev[1] = p0.y; en.prev[2] = p1.x;
+                            en.prev[3] = p1.y; en.prev[4] = p2.x; en.prev[5] = p2.y;
+                        } else {  // list full (thousands of flagged bodies per CTA): on the spot
+                            const ExactStepOut o = redo_exact<kLayout, kParam>(a, bi, env.surface_z);
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) {
+                                F[k] = S(o.F[k]);
+                                T[k] = S(o.T[k]);
+                            }
+                        }
+                    }
+                }
             }
 
             using V2 = typename Vec2Of<S>::type;
@@ -694,7 +858,55 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
             }
         }
     }
-    if (tid == 0) bulk_wait_all<0>();
+    if (sizeof(S) == 4 && !kCopyOnly) {
+        __syncthreads();  // every tile done: the list is complete, every bulk store has been issued
+        const int n_redo = *redo_count < REDO_CAP ? *redo_count : REDO_CAP;
+        if (n_redo > 0) {  // CTA-uniform
+            // scratch = the input stage (no load is in flight any more): [entry][role][ROLE_DOUBLES] doubles
+            double* const scratch = reinterpret_cast<double*>(smem + SM::OFF_IN);
+            static_assert(size_t(REDO_CAP) * N_ROLES * ROLE_DOUBLES * sizeof(double) <= SM::IN_BYTES || sizeof(S) != 4,
+                          "re-evaluation scratch must fit the input stage");
+            const int warp = tid >> 5, lane = tid & 31, n_warps = kThreads / 32;
+            for (int role = warp; role < N_ROLES; role += n_warps)
+                if (lane < n_redo)
+                    redo_role<kLayout, kParam>(role, a, redo_list[lane].body, env.surface_z, redo_list[lane].prev,
+                                               scratch + (lane * N_ROLES + role) * ROLE_DOUBLES);
+            __syncthreads();
+            ExactStepOut o;
+            long long bi = 0;
+            if (tid < n_redo) {
+                bi = redo_list[tid].body;
+                o = combine_roles(scratch + tid * N_ROLES * ROLE_DOUBLES);
+            }
+            if (tid == 0) bulk_wait_all<0>();  // the fast-path values of these bodies have landed ...
+            __syncthreads();
+            if (tid < n_redo) {                // ... and are replaced
+                float* of = reinterpret_cast<float*>(a.out_force) + 3 * bi;
+                float* ot = reinterpret_cast<float*>(a.out_torque) + 3 * bi;
+                if (kRobot) {
+                    // the per-robot sums were formed from the fast-path values: add the difference
+                    constexpr int EP = TL::E_POS;
+                    const float* pos = reinterpret_cast<const float*>(a.pos);
+                    const long long rb = bi / bpr;
+                    const float* pb = pos + EP * (rb * bpr);
+                    const float* pi = pos + EP * bi;
+                    const float ax = pi[0] - pb[0], ay = pi[1] - pb[1], az = pi[2] - pb[2];
+                    const float dfx = o.F[0] - of[0], dfy = o.F[1] - of[1], dfz = o.F[2] - of[2];
+                    float* ow = reinterpret_cast<float*>(a.out_wrench) + rb * 6;
+                    atomicAdd(ow + 0, dfx); atomicAdd(ow + 1, dfy); atomicAdd(ow + 2, dfz);
+                    atomicAdd(ow + 3, (o.T[0] - ot[0]) + (ay * dfz - az * dfy));
+                    atomicAdd(ow + 4, (o.T[1] - ot[1]) + (az * dfx - ax * dfz));
+                    atomicAdd(ow + 5, (o.T[2] - ot[2]) + (ax * dfy - ay * dfx));
+                }
+                of[0] = o.F[0]; of[1] = o.F[1]; of[2] = o.F[2];
+                ot[0] = o.T[0]; ot[1] = o.T[1]; ot[2] = o.T[2];
+            }
+        } else if (tid == 0) {
+            bulk_wait_all<0>();
+        }
+    } else if (tid == 0) {
+        bulk_wait_all<0>();
+    }
     if (kStats && a.stats) flush_stats(st, a.stats);
 }
 
@@ -745,7 +957,7 @@ __global__ void __launch_bounds__(256) step_direct_kernel(const __grid_constant_
         if (a.am_dense)
             bin.am_dense = reinterpret_cast<const S*>(a.am_dense) + 36 * a.am_slot_type[(a.first_body + i) % a.am_n_slots];
         S F[3], T[3];
-        step_one_body<S, kLayout, kParam, kStats>(a, i, bin, cl[10], env.surface_z, F, T, st);
+        step_one_body<S, kLayout, kParam, kStats, false>(a, i, bin, cl[10], env.surface_z, F, T, st);
         S* of = reinterpret_cast<S*>(a.out_force) + 3 * i;
         S* ot = reinterpret_cast<S*>(a.out_torque) + 3 * i;
         of[0] = F[0]; of[1] = F[1]; of[2] = F[2];
@@ -1054,7 +1266,7 @@ __global__ void rollout_persistent_kernel(const __grid_constant__ RolloutArgs a)
             double ratio;
             bool redo = body_step<S>(bin, cl[10], F, T, clamped, still, ratio);
             if (sizeof(S) == 4) {
-                redo = redo && !a.no_fallback;
+                redo = redo && a.no_fallback != 1;
                 if (redo) {
                     RawBody<float> rf;
                     rf.px = float(r.px); rf.py = float(r.py); rf.pz = float(r.pz);
@@ -1066,12 +1278,8 @@ __global__ void rollout_persistent_kernel(const __grid_constant__ RolloutArgs a)
                     float cf[N_COEFF];
 #pragma unroll
                     for (int k = 0; k < N_COEFF; ++k) cf[k] = float(cl[k]);
-                    ExactStepConsts kc;
-                    kc.rho = a.rho; kc.grav = a.grav; kc.inv_dt = 1.0 / a.dt; kc.surface_z = a.surface_z;
-                    kc.cx = float(a.current[0]); kc.cy = float(a.current[1]); kc.cz = float(a.current[2]);
-                    kc.quat_wxyz = a.quat_wxyz;
-                    kc.am_dense = nullptr;
-                    const ExactStepOut o = body_step_exact_f32(rf, cf, kc);
+                    const ExactStepOut o = body_step_exact_f32(rf, cf, a.quat_wxyz, a.rho, a.grav, 1.0 / a.dt, a.surface_z,
+                                                               float(a.current[0]), float(a.current[1]), float(a.current[2]));
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
                         F[k] = S(o.F[k]);

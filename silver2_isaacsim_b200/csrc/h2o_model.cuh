@@ -31,6 +31,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define H2O_HD __host__ __device__ __forceinline__
@@ -51,40 +52,109 @@ H2O_HD double h2o_min(double a, double b) { return fmin(a, b); }
 H2O_HD float h2o_max(float a, float b) { return fmaxf(a, b); }
 H2O_HD double h2o_max(double a, double b) { return fmax(a, b); }
 
-// 1/x, x > 0
+// Host stand-in for a MUFU approximation: the exact value times (1 + u 2^-22), u in [-1, 1) hashed from the
+// argument, so that the CPU precision studies see the error level of rcp.approx / rsqrt.approx (<= 2^-22.x).
+#if !defined(__CUDA_ARCH__)
+inline float h2o_mufu_noise(float exact, float arg)
+{
+    uint32_t h;
+    memcpy(&h, &arg, 4);
+    h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
+    const float u = float(int32_t(h)) * (1.0f / 2147483648.0f);
+    return exact * (1.0f + u * 2.3841858e-7f);
+}
+#endif
+
+// 1/x, x > 0: MUFU.RCP + one Newton step (full fp32 accuracy for normal, positive arguments; no IEEE
+// special-case slow path).  Without the step (-DH2O_NO_NEWTON) the fast path's error doubles and the conditioning
+// check would have to flag 2 % of the bodies instead of 0.02 % (tests/harness/flag_study.py).
 H2O_HD float h2o_rcp(float x)
 {
 #if defined(__CUDA_ARCH__)
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return fmaf(r, fmaf(-x, r, 1.0f), r);
+#if !defined(H2O_NO_NEWTON)
+    r = fmaf(r, fmaf(-x, r, 1.0f), r);
+#endif
+    return r;
+#else
+#if defined(H2O_NO_NEWTON)
+    return h2o_mufu_noise(1.0f / x, x);
 #else
     return 1.0f / x;
 #endif
+#endif
 }
-H2O_HD double h2o_rcp(double x) { return 1.0 / x; }
+// fp64 on the device: MUFU seed + two Newton steps (full double accuracy for normal, positive arguments)
+// instead of the IEEE division / square-root slow paths (~80 instructions each; the float64
+// re-evaluation of flagged bodies is latency-critical, see body_wrench_fast).
+H2O_HD double h2o_rcp(double x)
+{
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+#else
+    return 1.0 / x;
+#endif
+}
 
-// 1/sqrt(x), x > 0
+// 1/sqrt(x), x > 0: MUFU.RSQ + one Newton step (see h2o_rcp)
 H2O_HD float h2o_rsqrt(float x)
 {
 #if defined(__CUDA_ARCH__)
     float y;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+#if !defined(H2O_NO_NEWTON)
     const float t = x * y;
-    return fmaf(0.5f * y, fmaf(-t, y, 1.0f), y);
+    y = fmaf(0.5f * y, fmaf(-t, y, 1.0f), y);
+#endif
+    return y;
+#else
+#if defined(H2O_NO_NEWTON)
+    return h2o_mufu_noise(1.0f / sqrtf(x), x);
 #else
     return 1.0f / sqrtf(x);
 #endif
+#endif
 }
-H2O_HD double h2o_rsqrt(double x) { return 1.0 / sqrt(x); }
+H2O_HD double h2o_rsqrt(double x)
+{
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    y = fma(y, fma(-hx * y, y, 0.5), y);
+    y = fma(y, fma(-hx * y, y, 0.5), y);
+    y = fma(y, fma(-hx * y, y, 0.5), y);
+    return y;
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
 
-// sqrt(x) given r = h2o_rsqrt(x):  x*r, with one correction step in fp32
+// sqrt(x) given r = h2o_rsqrt(x):  x*r with one correction step
 H2O_HD float h2o_sqrt_from_rsqrt(float x, float r)
 {
     const float s = x * r;
+#if !defined(H2O_NO_NEWTON)
     return fmaf(fmaf(-s, s, x), 0.5f * r, s);
+#else
+    return s;
+#endif
 }
-H2O_HD double h2o_sqrt_from_rsqrt(double x, double) { return sqrt(x); }
+H2O_HD double h2o_sqrt_from_rsqrt(double x, double r)
+{
+#if defined(__CUDA_ARCH__)
+    const double s = x * r;
+    return fma(fma(-s, s, x), 0.5 * r, s);
+#else
+    (void)r;
+    return sqrt(x);
+#endif
+}
 
 // 1/x for the waterline ratio (H precision).  Device: approximation + two Newton steps.
 H2O_HD double h2o_rcp_h(double x)
@@ -135,7 +205,8 @@ H2O_HD void h2o_or_if_less(uint32_t& mask, float t, float m, uint32_t bit)
 template <bool kExactTrig> H2O_HD double lift_coefficient_of(double d, double one_minus_d2)
 {
     if (kExactTrig) return sin(2.0 * asin(d));
-    return 2.0 * d * sqrt(fmax(0.0, one_minus_d2));
+    const double x = fmax(one_minus_d2, 1e-300);
+    return 2.0 * d * h2o_sqrt_from_rsqrt(x, h2o_rsqrt(x));
 }
 template <bool kExactTrig> H2O_HD float lift_coefficient_of(float d, float one_minus_d2)
 {
@@ -209,26 +280,23 @@ template <typename H, typename L> struct Terms {
     bool still;           // wet and speed <= 1e-6: the reference raises here
 };
 
-// One body, branch-free.  kExactTrig: asin/sin as the reference vs 2d*sqrt(1-d^2).
-template <typename H, typename L, bool kExactTrig>
-H2O_HD void body_terms(const BodyIn<H, L>& in, Terms<H, L>& t)
+// ---- waterline: 27 keypoints {-hx,0,hx}x{hy,0,-hy}x{hz,0,-hz} against the plane z = 0
+//      (numba_hydrodynamics_wrapper.py:55-73, numba_hydrodynamics.py:271, :59-105), all in H.
+// A keypoint's height is p_z + (i a + j b) + k c with a = R20 hx, b = R21 hy, c = R22 hz: 13 sums up to
+// sign, 27 strict compares build the submerged mask; z_min / z_max = p_z -+ (|a| + |b| + |c|).
+template <typename H> struct Waterline {
+    uint32_t mask;   // 27-bit submerged-keypoint mask, bit layout kp_bit()
+    H ratio;         // submersion ratio after the 1e-9 cut (numba_hydrodynamics.py:87, :277-279)
+    bool partial;    // z_min < 0 < z_max: the centre of buoyancy is the mean of the wet keypoints
+};
+template <typename H>
+H2O_HD void waterline(H pz, H r20h, H r21h, H r22h, H dxh, H dyh, H dzh, Waterline<H>& w)
 {
-    // ---- rotation (numba_hydrodynamics.py:14-49).  Row 2 in H for the waterline.
-    const H hx2 = in.qx + in.qx, hy2 = in.qy + in.qy, hz2 = in.qz + in.qz;
-    const H r20h = in.qx * hz2 - in.qw * hy2;
-    const H r21h = in.qy * hz2 + in.qw * hx2;
-    const H r22h = H(1) - (in.qx * hx2 + in.qy * hy2);
-    // |q|^2 - 1: the reference never normalises, so R is orthogonal only up to this.
-    const H dqh = ((in.qx * in.qx + in.qy * in.qy) + (in.qz * in.qz + in.qw * in.qw)) - H(1);
-
-    // ---- waterline: 27 keypoints {-hx,0,hx}x{hy,0,-hy}x{hz,0,-hz}
-    //      (numba_hydrodynamics_wrapper.py:55-73, numba_hydrodynamics.py:271, :59-105)
-    const H dxh = H(in.dimx), dyh = H(in.dimy), dzh = H(in.dimz);
     const H a = r20h * (dxh * H(0.5));
     const H b = r21h * (dyh * H(0.5));
     const H c = r22h * (dzh * H(0.5));
     const H abp = a + b, abm = a - b;
-    const H m = -in.pz;  // keypoint wet  <=>  fl(t + pz) < 0  <=>  t < -pz  (exact)
+    const H m = -pz;  // keypoint wet  <=>  fl(t + pz) < 0  <=>  t < -pz  (exact)
     uint32_t mask = 0;
 #define H2O_KP(i, j, k, tval)                                                   \
     {                                                                           \
@@ -253,13 +321,37 @@ H2O_HD void body_terms(const BodyIn<H, L>& in, Terms<H, L>& t)
     h2o_or_if_less(mask, H(0), m, 1u << kp_bit(0, 0, 0));
 
     const H ext = (h2o_abs(a) + h2o_abs(b)) + h2o_abs(c);  // highest keypoint above p
-    const H z_min = in.pz - ext, z_max = in.pz + ext;
+    const H z_min = pz - ext, z_max = pz + ext;
     const bool dry = z_min >= H(0);
     const bool partial = !dry && !(z_max <= H(0));
     const H total_height = z_max - z_min;
     H ratio = H(1);
     if (partial && !(total_height < H(1e-6))) ratio = h2o_min(H(1), -z_min * h2o_rcp_h(total_height));
     if (dry || !(ratio > H(1e-9))) ratio = H(0);  // numba_hydrodynamics.py:87, :277-279
+    w.mask = mask;
+    w.ratio = ratio;
+    w.partial = partial;
+}
+
+// One body, branch-free.  kExactTrig: asin/sin as the reference vs 2d*sqrt(1-d^2).
+template <typename H, typename L, bool kExactTrig>
+H2O_HD void body_terms(const BodyIn<H, L>& in, Terms<H, L>& t, const Waterline<H>* given = nullptr)
+{
+    // ---- rotation (numba_hydrodynamics.py:14-49).  Row 2 in H for the waterline.
+    const H hx2 = in.qx + in.qx, hy2 = in.qy + in.qy, hz2 = in.qz + in.qz;
+    const H r20h = in.qx * hz2 - in.qw * hy2;
+    const H r21h = in.qy * hz2 + in.qw * hx2;
+    const H r22h = H(1) - (in.qx * hx2 + in.qy * hy2);
+    // |q|^2 - 1: the reference never normalises, so R is orthogonal only up to this.
+    const H dqh = ((in.qx * in.qx + in.qy * in.qy) + (in.qz * in.qz + in.qw * in.qw)) - H(1);
+
+    const H dxh = H(in.dimx), dyh = H(in.dimy), dzh = H(in.dimz);
+    Waterline<H> wl;
+    if (given) wl = *given;  // a caller that has run the identical H arithmetic already (body_wrench_fast)
+    else waterline<H>(in.pz, r20h, r21h, r22h, dxh, dyh, dzh, wl);
+    const uint32_t mask = wl.mask;
+    const H ratio = wl.ratio;
+    const bool partial = wl.partial;
 
     t.kp_mask = mask;
     t.ratio = ratio;
@@ -486,7 +578,7 @@ template <typename H, typename L>
 H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], bool& clamped, H& ratio_out,
                              bool& still, bool& suspect, L* diag = nullptr)
 {
-    // ---- waterline in H (identical to body_terms)
+    // ---- waterline in H (the same function body_terms calls)
     const H hx2 = in.qx + in.qx, hy2 = in.qy + in.qy, hz2 = in.qz + in.qz;
     const H hxx = in.qx * hx2, hyy = in.qy * hy2, hzz = in.qz * hz2;
     const H hxy = in.qx * hy2, hxz = in.qx * hz2, hyz = in.qy * hz2;
@@ -496,41 +588,11 @@ H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], boo
     const H r22h = H(1) - (hxx + hyy);
     const H dqh = ((in.qx * in.qx + in.qy * in.qy) + (in.qz * in.qz + in.qw * in.qw)) - H(1);
     const H dxh = H(in.dimx), dyh = H(in.dimy), dzh = H(in.dimz);
-    const H a = r20h * (dxh * H(0.5));
-    const H b = r21h * (dyh * H(0.5));
-    const H c = r22h * (dzh * H(0.5));
-    const H abp = a + b, abm = a - b;
-    const H m = -in.pz;
-    uint32_t mask = 0;
-#define H2O_KP(i, j, k, tval)                                                   \
-    {                                                                           \
-        const H tv = (tval);                                                    \
-        h2o_or_if_less(mask, tv, m, 1u << kp_bit(i, j, k));                     \
-        h2o_or_if_less(mask, -tv, m, 1u << kp_bit(-(i), -(j), -(k)));           \
-    }
-    H2O_KP(1, 0, 0, a)
-    H2O_KP(0, 1, 0, b)
-    H2O_KP(1, 1, 0, abp)
-    H2O_KP(1, -1, 0, abm)
-    H2O_KP(0, 0, 1, c)
-    H2O_KP(1, 0, 1, a + c)
-    H2O_KP(1, 0, -1, a - c)
-    H2O_KP(0, 1, 1, b + c)
-    H2O_KP(0, 1, -1, b - c)
-    H2O_KP(1, 1, 1, abp + c)
-    H2O_KP(1, 1, -1, abp - c)
-    H2O_KP(1, -1, 1, abm + c)
-    H2O_KP(1, -1, -1, abm - c)
-#undef H2O_KP
-    h2o_or_if_less(mask, H(0), m, 1u << kp_bit(0, 0, 0));
-    const H ext = (h2o_abs(a) + h2o_abs(b)) + h2o_abs(c);
-    const H z_min = in.pz - ext, z_max = in.pz + ext;
-    const bool dry = z_min >= H(0);
-    const bool partial = !dry && !(z_max <= H(0));
-    const H total_height = z_max - z_min;
-    H ratio = H(1);
-    if (partial && !(total_height < H(1e-6))) ratio = h2o_min(H(1), -z_min * h2o_rcp_h(total_height));
-    if (dry || !(ratio > H(1e-9))) ratio = H(0);
+    Waterline<H> wl;
+    waterline<H>(in.pz, r20h, r21h, r22h, dxh, dyh, dzh, wl);
+    const uint32_t mask = wl.mask;
+    const H ratio = wl.ratio;
+    const bool partial = wl.partial;
     ratio_out = ratio;
     const L rl = L(ratio);
     const H fbz = in.rho_h * (ratio * (dxh * dyh * dzh)) * in.grav_h;  // numba_hydrodynamics.py:282
@@ -615,6 +677,8 @@ H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], boo
     const L tdx = (gd1 * d2) * (w1 - w2) + k4 * (gby * s2 - gbz * s1) + nf * (d1 * cbz - d2 * cby);
     const L tdy = (gd2 * d0) * (w2 - w0) + k4 * (gbz * s0 - gbx * s2) + nf * (d2 * cbx - d0 * cbz);
     const L tdz = (gd0 * d1) * (w0 - w1) + k4 * (gbx * s1 - gby * s0) + nf * (d0 * cby - d1 * cbx);
+    // running sum of the torque groups' magnitudes (conditioning check at the end)
+    L mt = h2o_abs(psi) * ((h2o_abs(tdx) + h2o_abs(tdy)) + h2o_abs(tdz));
 
     // ---- lift in the body frame: axis = d x z = (d1,-d0,0), dir = axis/|axis| x d
     const L an2 = d0 * d0 + d1 * d1;
@@ -661,12 +725,14 @@ H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], boo
     tbx = psi * tdx + (cfx - ai0);
     tby = psi * tdy + (cfy - ai1);
     tbz = psi * tdz + (cfz - ai2);
+    mt += ((h2o_abs(cfx) + h2o_abs(cfy)) + h2o_abs(cfz)) + ((h2o_abs(ai0) + h2o_abs(ai1)) + h2o_abs(ai2));
 
     // ---- angular drag (world): -(0.5 rho |w| C V + k min(1, 5|w|)) ratio * w
     const L as2 = in.wx * in.wx + in.wy * in.wy + in.wz * in.wz;
     const L as = h2o_sqrt_from_rsqrt(as2, h2o_rsqrt(h2o_max(as2, L(1e-30))));
     const L aq = (as > L(1e-6)) ? L(0.5) * in.rho * as * in.c_drag_ang * vol : L(0);
     const L ka = (aq + in.k_damp_ang * h2o_min(L(1), as * L(5.0))) * rl;
+    mt += ka * as + (h2o_abs(tbuoy_x) + h2o_abs(tbuoy_y));
 
     T[0] = ((r00 * tbx + r01 * tby + r02 * tbz) - ka * in.wx) + tbuoy_x;
     T[1] = ((r10 * tbx + r11 * tby + r12 * tbz) - ka * in.wy) + tbuoy_y;
@@ -686,10 +752,6 @@ H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], boo
     // world-frame formulation (body_terms + net_wrench), so fp32 mode stays inside its bound for EVERY body.
     L flag_kt, flag_kf;
     {
-        const L mt = ((h2o_abs(psi) * ((h2o_abs(tdx) + h2o_abs(tdy)) + h2o_abs(tdz)) +
-                       ((h2o_abs(cfx) + h2o_abs(cfy)) + h2o_abs(cfz))) +
-                      ((h2o_abs(ai0) + h2o_abs(ai1)) + h2o_abs(ai2))) +
-                     ((ka * ((h2o_abs(in.wx) + h2o_abs(in.wy)) + h2o_abs(in.wz))) + (h2o_abs(tbuoy_x) + h2o_abs(tbuoy_y)));
         const L t1 = (h2o_abs(T[0]) + h2o_abs(T[1])) + h2o_abs(T[2]);
         const L f1 = (h2o_abs(F[0]) + h2o_abs(F[1])) + h2o_abs(F[2]);
         // (b): buoyancy is the only force group that does not vanish with the velocities, so a cancelled net
