@@ -697,6 +697,24 @@ def side_measurements(torch, W, dev, dtype_main):
     out["c5_small_batch_1024x1000"] = c5
     del e5
     if dtype_main == torch.float32:
+        # the headline workload with strict mode off (flagged bodies keep their fp32 result): what the
+        # float64 re-evaluation costs, and what it buys (parity of the same sample, both ways)
+        from oracle import hydro_oracle as O
+        from tests import scoring
+        n = 1 << 20
+        bs = make_batches(torch, W, n, 6, torch.float32, dev, W.SEED_BASE + 3)
+        res = {}
+        for strict in (True, False):
+            for b in bs:
+                b[0].set_strict(strict)
+            region, _ = build_step_region(torch, [(lambda b=b: b[0].step_bound(b[1].dt)) for b in bs], 24, dev)
+            ms = timeit(region, 1, rounds=41) / 24
+            eng_p = lambda m, strict=strict: _with(HydroEngine(m, dtype=torch.float32, device=dev), lambda e: e.set_strict(strict))
+            par = parity_sample(torch, O, scoring, eng_p, bs[0][1], dev, sample=1 << 20)
+            res["strict" if strict else "fast"] = {"us_per_step": 1e3 * ms, "achieved_gbs": BYTES_PER_BODY_F32 * n / (ms * 1e-3) / 1e9,
+                                                   "parity_1M_bodies": {k: par[k] for k in ("pass_F", "pass_T", "worst_x_tol")}}
+        out["c3_strict_vs_fast"] = res
+        del bs
         # C3 at 4x the bodies: the per-launch ramp-up / drain amortises
         n4 = 1 << 22
         bs = make_batches(torch, W, n4, 2, torch.float32, dev, W.SEED_BASE + 400)
@@ -731,6 +749,11 @@ def side_measurements(torch, W, dev, dtype_main):
                                "achieved_gbs": 2 * BYTES_PER_BODY_F32 * n / (ms64 * 1e-3) / 1e9}
         del bs
     return out
+
+
+def _with(obj, fn):
+    fn(obj)
+    return obj
 
 
 def e5_free_eager(e, wl, steps):

@@ -151,6 +151,12 @@ H2O_API int h2o_set_kernel(h2o_handle h, int choice);
  * for the added-mass terms (:216-217) and cob = cop = position for a dry body (:59-61, :290).
  * Default 0 = the Numba semantics, which every other entry point always follows. */
 H2O_API int h2o_set_warp_compat(h2o_handle h, int enable);
+/* fp32 mode only.  1 (default): every body meets the fp32-mode bound of the parity criterion (|dF|, |dtau| <=
+ * max(1e-5 |.|_inf, 1e-6) against the float64 Numba path): the fused step flags the few bodies per 10 000 whose
+ * force / torque groups cancel (or whose quaternion is far from unit) and re-evaluates them in float64 with the
+ * world-frame formulation of solve_hydrodynamics (numba_hydrodynamics.py:255-314).  0: flagged bodies keep their
+ * fp32 result (about one body per million then misses the bound by up to 3x); saves the re-evaluation tail. */
+H2O_API int h2o_set_strict(h2o_handle h, int enable);
 /* Tuning knob: tile-kernel variant (threads per CTA / TMA stages); 0 = built-in default. */
 H2O_API int h2o_set_tile_config(h2o_handle h, int cfg);
 /* Accumulate global statistics inside the step kernel (device-side, no host sync). */
@@ -239,14 +245,26 @@ H2O_API int h2o_components(h2o_handle h, const void* pos, const void* quat, cons
                            void* const out8[8], void* out_sub_ratio, int32_t* out_flags,
                            h2o_stream stream);
 
-/* ---- host-buffer convenience path ------------------------------------------------------
- * Numba-wrapper style call with HOST arrays (the reference's CPU flavour takes and returns
- * NumPy arrays): chunked, double-buffered H2D -> step -> D2H on internal streams.  Synchronous:
- * waits for previously queued device work on entry and returns after the results are in the
- * host buffers. */
+/* ---- host-buffer path --------------------------------------------------------------------
+ * Numba-wrapper style call with HOST arrays (the reference's CPU flavour takes and returns NumPy arrays,
+ * numba_hydrodynamics_wrapper.py:34-53).  Synchronous: ordered after the work queued before on the
+ * blocking streams (an event on the legacy default stream, no device-wide synchronisation), returns when
+ * the results are in the host buffers.
+ *   - pinned (page-locked) host buffers, 16-byte aligned: ZERO-COPY.  The fused tile kernel runs directly on
+ *     them: its TMA bulk loads pull each tile over PCIe into shared memory, its bulk stores push force /
+ *     torque back -- one kernel, transfers overlapped with the arithmetic tile by tile, no staging copy.
+ *   - pageable buffers: staged through engine-owned pinned memory, chunked H2D -> step -> D2H pipeline on
+ *     three streams.
+ * h2o_last_host_path reports which one the last call took (1 zero-copy, 2 staged). */
 H2O_API int h2o_step_host(h2o_handle h, const void* pos, const void* quat, const void* lin_vel,
                           const void* ang_vel, double dt, void* out_force, void* out_torque,
                           void* out_robot_wrench);
+/* Same with the PhysX tensor-API layout on the host: transforms (N,7) = [p, q], velocities (N,6) = [v, w]
+ * (what RigidPrimView.get_world_poses / get_velocities hand out when the simulation runs on the CPU,
+ * hydrodynamics_behavior.py:178-189): two input arrays instead of four. */
+H2O_API int h2o_step_host_physx(h2o_handle h, const void* transforms, const void* velocities, double dt,
+                                void* out_force, void* out_torque, void* out_robot_wrench);
+H2O_API int h2o_last_host_path(h2o_handle h);
 
 /* ---- statistics / introspection ----------------------------------------------------------- */
 H2O_API int h2o_stats_device_ptr(h2o_handle h, void** out_ptr); /* H2O_N_STATS doubles on device */

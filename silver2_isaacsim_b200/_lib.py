@@ -11,7 +11,8 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libh2o_b200.so")
+# H2O_LIB_PATH: tuning experiments load a variant build (csrc/Makefile TAG=...); the product is the default path
+LIB_PATH = os.environ.get("H2O_LIB_PATH") or os.path.join(_HERE, "lib", "libh2o_b200.so")
 
 # h2o_status (include/h2o.h)
 H2O_OK = 0
@@ -60,6 +61,7 @@ SIGNATURES = {
     "h2o_set_kernel": (c_int, [_P, c_int]),
     "h2o_set_tile_config": (c_int, [_P, c_int]),
     "h2o_set_warp_compat": (c_int, [_P, c_int]),
+    "h2o_set_strict": (c_int, [_P, c_int]),
     "h2o_enable_stats": (c_int, [_P, c_int]),
     "h2o_reset": (c_int, [_P, _P]),
     "h2o_set_prev": (c_int, [_P, _P, _P, _P]),
@@ -77,6 +79,8 @@ SIGNATURES = {
     "h2o_integrate_free_bodies": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_double, c_double, _P]),
     "h2o_components": (c_int, [_P, _P, _P, _P, _P, _P, _P, POINTER(c_void_p), _P, _P, _P]),
     "h2o_step_host": (c_int, [_P, _P, _P, _P, _P, c_double, _P, _P, _P]),
+    "h2o_step_host_physx": (c_int, [_P, _P, _P, c_double, _P, _P, _P]),
+    "h2o_last_host_path": (c_int, [_P]),
     "h2o_stats_device_ptr": (c_int, [_P, POINTER(c_void_p)]),
     "h2o_read_stats": (c_int, [_P, POINTER(c_double), c_int, _P]),
     "h2o_launch_count": (c_int64, [_P]),

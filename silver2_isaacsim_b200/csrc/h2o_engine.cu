@@ -63,6 +63,7 @@ struct h2o_engine {
     int n_slots = 0, n_types = 0;
     void* prev = nullptr;
     double* stats = nullptr;
+    uint32_t* redo_bitmap = nullptr;  // one bit per body, all zero between launches (tile kernel, deferred-list overflow)
     bool stats_on = false;
     int bodies_per_robot = 0;
     int quat_order = H2O_QUAT_XYZW;
@@ -97,7 +98,10 @@ struct h2o_engine {
     // host pipeline
     void* hp_dev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // pos quat lin ang F T W
     void* hp_pin[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t hp_dev_bytes[4] = {0, 0, 0, 0}, hp_pin_bytes[4] = {0, 0, 0, 0};
     cudaStream_t hp_stream[HOST_PIPE_STREAMS] = {nullptr, nullptr, nullptr};
+    cudaEvent_t hp_event = nullptr;
+    int last_host_path = 0;  // 1 = zero-copy (kernel on the pinned host buffers), 2 = staged chunk pipeline
     cudaStream_t capture_stream = nullptr;  // graph capture never runs on the caller's (maybe legacy) stream
     int no_fallback = 0;       // study knob (H2O_NO_FALLBACK=1): flagged bodies keep their fast-path result
     bool dry_run = false;  // launch helpers do their one-time attribute / occupancy set-up and count, but launch nothing
@@ -150,8 +154,14 @@ template <int T, int I, int O, int MB, bool CO = false, int BPR = 0> struct Cfg 
     static constexpr bool kCopyOnly = CO;  // measurement aid: memory traffic without arithmetic
     static constexpr int kBpr = BPR;       // robot mode specialised for this robot size (0 = run time)
 };
+#ifndef H2O_MB_DEFAULT
+#define H2O_MB_DEFAULT 6
+#endif
+#ifndef H2O_MB_HEXAPOD
+#define H2O_MB_HEXAPOD 4
+#endif
 template <typename S> struct DefaultCfg;
-template <> struct DefaultCfg<float> { using type = Cfg<128, 1, 2, 6>; };
+template <> struct DefaultCfg<float> { using type = Cfg<128, 1, 2, H2O_MB_DEFAULT>; };
 template <> struct DefaultCfg<double> { using type = Cfg<64, 1, 2, 6>; };
 // With an articulation a tile holds whole robots (and whole 16-byte granules), e.g. 19-body
 // hexapods -> multiples of 76 bodies.  Several CTA sizes are compiled and the one whose lanes are
@@ -163,7 +173,7 @@ template <> struct RobotCfgs<float> {
     using A = Cfg<128, 1, 2, 6>;
     using B = Cfg<160, 1, 2, 4>;
     using C = Cfg<256, 1, 2, 3>;
-    using Hexapod = Cfg<160, 1, 2, 4, false, HEXAPOD_BODIES>;  // = B with the robot size compiled in
+    using Hexapod = Cfg<160, 1, 2, H2O_MB_HEXAPOD, false, HEXAPOD_BODIES>;  // = B with the robot size compiled in
 };
 template <> struct RobotCfgs<double> {
     using A = Cfg<64, 1, 2, 6>;
@@ -446,6 +456,7 @@ static int step_device(h2o_engine* e, int layout, const void* pos, const void* q
     a.am_dense = e->am_dense; a.am_slot_type = e->am_slot_type; a.am_n_slots = e->am_slots;
     a.robot_offsets = e->robot_offsets; a.n_robots_var = e->n_robots_var;
     a.no_fallback = e->no_fallback;
+    a.redo_bitmap = e->redo_bitmap;
     a.surface_eta = e->surface_eta ? static_cast<const char*>(e->surface_eta) + size_t(first_body) * e->esz : nullptr;
     return e->dtype == H2O_F32 ? step_typed<float>(e, layout, a, stream) : step_typed<double>(e, layout, a, stream);
 }
@@ -506,13 +517,17 @@ int h2o_create(h2o_handle* out, int64_t n_bodies, int dtype, int device)
     if (const char* v = getenv("H2O_PDL")) e->use_pdl = atoi(v) != 0;
     if (const char* v = getenv("H2O_NO_FALLBACK")) e->no_fallback = std::max(0, atoi(v));
     if (const char* v = getenv("H2O_ROBOT_CFG")) e->robot_cfg = std::max(-1, std::min(2, atoi(v)));
+    const size_t bitmap_bytes = (size_t(n_bodies) / 32 + 2) * sizeof(uint32_t);
     if (cudaMalloc(&e->prev, size_t(n_bodies) * 6 * e->esz) != cudaSuccess ||
         cudaMalloc(reinterpret_cast<void**>(&e->stats), N_STATS * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&e->redo_bitmap), bitmap_bytes) != cudaSuccess ||
+        cudaMemset(e->redo_bitmap, 0, bitmap_bytes) != cudaSuccess ||
         cudaMemset(e->prev, 0, size_t(n_bodies) * 6 * e->esz) != cudaSuccess ||
         cudaMemset(e->stats, 0, N_STATS * sizeof(double)) != cudaSuccess) {
         const cudaError_t why = cudaGetLastError();
         if (e->prev) cudaFree(e->prev);
         if (e->stats) cudaFree(e->stats);
+        if (e->redo_bitmap) cudaFree(e->redo_bitmap);
         delete e;
         return fail(H2O_ERR_CUDA, "allocating the engine state for %lld bodies failed: %s", (long long)n_bodies,
                     cudaGetErrorString(why));
@@ -534,6 +549,7 @@ int h2o_destroy(h2o_handle h)
     }
     for (int i = 0; i < HOST_PIPE_STREAMS; ++i)
         if (e->hp_stream[i]) cudaStreamDestroy(e->hp_stream[i]);
+    if (e->hp_event) cudaEventDestroy(e->hp_event);
     if (e->capture_stream) cudaStreamDestroy(e->capture_stream);
     if (e->coeff) cudaFree(e->coeff);
     if (e->slot_type) cudaFree(e->slot_type);
@@ -542,6 +558,7 @@ int h2o_destroy(h2o_handle h)
     if (e->robot_offsets) cudaFree(e->robot_offsets);
     if (e->prev) cudaFree(e->prev);
     if (e->stats) cudaFree(e->stats);
+    if (e->redo_bitmap) cudaFree(e->redo_bitmap);
     e->magic = 0;
     delete e;
     return H2O_OK;
@@ -818,6 +835,15 @@ int h2o_set_kernel(h2o_handle h, int choice)
     { DeviceGuard gi(e->device); invalidate_graph(e); }
     if (choice < H2O_KERNEL_AUTO || choice > H2O_KERNEL_DIRECT) return fail(H2O_ERR_BAD_ARGUMENT, "bad kernel choice");
     e->kernel_choice = choice;
+    return H2O_OK;
+}
+
+int h2o_set_strict(h2o_handle h, int enable)
+{
+    h2o_engine* e = check(h);
+    if (!e) return H2O_ERR_BAD_HANDLE;
+    { DeviceGuard gi(e->device); invalidate_graph(e); }
+    e->no_fallback = enable ? 0 : 1;
     return H2O_OK;
 }
 
@@ -1203,12 +1229,7 @@ int h2o_components(h2o_handle h, const void* pos, const void* quat, const void* 
 // ---- host-buffer pipeline --------------------------------------------------------------
 static int hp_init(h2o_engine* e)
 {
-    if (e->hp_dev[0]) return H2O_OK;
-    const size_t per[7] = {3, 4, 3, 3, 3, 3, 6};
-    for (int i = 0; i < 7; ++i) {
-        const size_t bytes = size_t(e->n) * per[i] * e->esz;
-        CUDA_TRY(cudaMalloc(&e->hp_dev[i], bytes));
-    }
+    if (e->hp_stream[0]) return H2O_OK;
     for (int i = 0; i < HOST_PIPE_STREAMS; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&e->hp_stream[i], cudaStreamNonBlocking));
     return H2O_OK;
 }
@@ -1223,39 +1244,98 @@ static bool is_pinned_or_device(const void* p)
     return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
-int h2o_step_host(h2o_handle h, const void* pos, const void* quat, const void* lin_vel, const void* ang_vel,
-                  double dt, void* out_force, void* out_torque, void* out_robot_wrench)
+// Device-side alias of a pinned (page-locked, mapped) host buffer, or nullptr if `p` is anything else.
+static void* mapped_alias(const void* p)
 {
-    h2o_engine* e = check(h);
-    if (!e) return H2O_ERR_BAD_HANDLE;
-    const void* in[4] = {pos, quat, lin_vel, ang_vel};
-    void* out[3] = {out_force, out_torque, out_robot_wrench};
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    return at.devicePointer;
+}
+
+// Host-buffer step.  `in` / `out` follow the layout: split = {pos, quat, lin, ang}, view = {pos, quat, vel6, -},
+// physx = {transforms7, -, vel6, -}; out = {force, torque, robot wrench or NULL}.
+//
+// Pinned host buffers take the ZERO-COPY path: the fused tile kernel is launched straight on them -- its TMA bulk
+// loads pull the tiles over PCIe into shared memory and its bulk stores push force / torque back, so transfer
+// and arithmetic overlap tile by tile inside one kernel, with no staging buffers, no chunk pipeline and no
+// pipeline tail (carried velocities and coefficients stay in HBM).  Pageable buffers are staged through
+// engine-owned pinned memory and a chunked H2D -> step -> D2H pipeline on three streams.
+static int step_host_impl(h2o_engine* e, int layout, const void* const in[4], void* const out[3], double dt)
+{
+    static const size_t widths[3][4] = {{3, 4, 3, 3}, {7, 0, 6, 0}, {3, 4, 6, 0}};
+    const size_t* per_in = widths[layout];
+    const size_t per_out[3] = {3, 3, 6};
     for (int i = 0; i < 4; ++i)
-        if (!in[i]) return fail(H2O_ERR_BAD_ARGUMENT, "NULL host input %d", i);
-    if (!out_force || !out_torque) return fail(H2O_ERR_BAD_ARGUMENT, "NULL host output");
-    if (out_robot_wrench && e->bodies_per_robot <= 0)
+        if (per_in[i] && !in[i]) return fail(H2O_ERR_BAD_ARGUMENT, "NULL host input %d", i);
+    if (!out[0] || !out[1]) return fail(H2O_ERR_BAD_ARGUMENT, "NULL host output");
+    if (out[2] && e->bodies_per_robot <= 0)
         return fail(H2O_ERR_NOT_CONFIGURED, "robot wrench requested but h2o_set_articulation not called");
     if (e->param_mode < 0) return fail(H2O_ERR_NOT_CONFIGURED, "no parameters set (h2o_set_params_*)");
     if (!(dt > 1e-6)) return H2O_OK;
     DeviceGuard g(e->device);
     if (int rc = hp_init(e)) return rc;
-    // The pipeline runs on engine-owned non-blocking streams and no caller stream is passed in:
-    // order it after whatever the caller queued before (h2o_set_prev, a previous h2o_step, ...).
-    CUDA_TRY(cudaDeviceSynchronize());
-    const size_t per_in[4] = {3, 4, 3, 3};
-    const size_t per_out[3] = {3, 3, 6};
+    // No caller stream is passed in: order the engine's streams after everything queued so far on the
+    // blocking streams (the legacy default stream synchronises with all of them) -- an event, not a
+    // device-wide host synchronisation.
+    if (!e->hp_event) CUDA_TRY(cudaEventCreateWithFlags(&e->hp_event, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(e->hp_event, cudaStreamLegacy));
+    for (int i = 0; i < HOST_PIPE_STREAMS; ++i) CUDA_TRY(cudaStreamWaitEvent(e->hp_stream[i], e->hp_event, 0));
 
-    // pageable host memory is staged through engine-owned pinned buffers
-    const void* src[4];
+    // ---- zero-copy path
+    {
+        void* din[4] = {nullptr, nullptr, nullptr, nullptr};
+        void* dout[3] = {nullptr, nullptr, nullptr};
+        bool ok = getenv("H2O_HOST_STAGED") == nullptr;
+        for (int i = 0; i < 4 && ok; ++i)
+            if (per_in[i]) ok = (din[i] = mapped_alias(in[i])) != nullptr && aligned16(din[i]);
+        for (int i = 0; i < 3 && ok; ++i)
+            if (out[i]) ok = (dout[i] = mapped_alias(out[i])) != nullptr && aligned16(dout[i]);
+        if (ok) {
+            cudaStream_t s = e->hp_stream[0];
+            int rc = step_device(e, layout, din[0], din[1], din[2], din[3], dt, dout[0], dout[1], dout[2], e->n, 0,
+                                 e->prev, coeff_at(e, 0), s);
+            if (rc) return rc;
+            CUDA_TRY(cudaStreamSynchronize(s));
+            e->last_host_path = 1;
+            return H2O_OK;
+        }
+    }
+    e->last_host_path = 2;
+
+    // ---- staged pipeline.  Pageable host memory goes through engine-owned pinned buffers.
+    const void* src[4] = {nullptr, nullptr, nullptr, nullptr};
     void* dst[3];
     bool stage_out[3] = {false, false, false};
     for (int i = 0; i < 4; ++i) {
+        if (!per_in[i]) continue;
+        const size_t bytes = size_t(e->n) * per_in[i] * e->esz;
+        if (e->hp_dev_bytes[i] < bytes) {
+            if (e->hp_dev[i]) cudaFree(e->hp_dev[i]);
+            e->hp_dev[i] = nullptr; e->hp_dev_bytes[i] = 0;
+            CUDA_TRY(cudaMalloc(&e->hp_dev[i], bytes));
+            e->hp_dev_bytes[i] = bytes;
+        }
         if (is_pinned_or_device(in[i])) src[i] = in[i];
         else {
-            const size_t bytes = size_t(e->n) * per_in[i] * e->esz;
-            if (!e->hp_pin[i]) CUDA_TRY(cudaMallocHost(&e->hp_pin[i], bytes));
+            if (e->hp_pin_bytes[i] < bytes) {
+                if (e->hp_pin[i]) cudaFreeHost(e->hp_pin[i]);
+                e->hp_pin[i] = nullptr; e->hp_pin_bytes[i] = 0;
+                CUDA_TRY(cudaMallocHost(&e->hp_pin[i], bytes));
+                e->hp_pin_bytes[i] = bytes;
+            }
             memcpy(e->hp_pin[i], in[i], bytes);
             src[i] = e->hp_pin[i];
+        }
+    }
+    {
+        const size_t per_dev_out[3] = {3, 3, 6};
+        for (int i = 0; i < 3; ++i) {
+            const size_t bytes = size_t(e->n) * per_dev_out[i] * e->esz;
+            if (!e->hp_dev[4 + i]) CUDA_TRY(cudaMalloc(&e->hp_dev[4 + i], bytes));
         }
     }
     for (int i = 0; i < 3; ++i) {
@@ -1270,7 +1350,7 @@ int h2o_step_host(h2o_handle h, const void* pos, const void* quat, const void* l
     }
 
     // chunking: whole tiles / whole robots per chunk, a few chunks per stream
-    const int bpr = (out_robot_wrench && e->bodies_per_robot > 0) ? e->bodies_per_robot : 0;
+    const int bpr = (out[2] && e->bodies_per_robot > 0) ? e->bodies_per_robot : 0;
     long long unit = tile_unit(e->esz, bpr);
     while (unit < 256) unit *= 2;  // whole robots and whole 16-byte granules per chunk
     if (e->n_slots > 1) unit = unit / gcd_ll(unit, e->n_slots) * e->n_slots;  // keep slot phase per chunk
@@ -1302,18 +1382,18 @@ int h2o_step_host(h2o_handle h, const void* pos, const void* quat, const void* l
         const long long b0 = bounds[k];
         const long long cnt = bounds[k + 1] - b0;
         cudaStream_t s = e->hp_stream[k % HOST_PIPE_STREAMS];
+        const void* dchunk[4] = {nullptr, nullptr, nullptr, nullptr};
         for (int i = 0; i < 4; ++i) {
+            if (!per_in[i]) continue;
             const size_t off = size_t(b0) * per_in[i] * e->esz;
             CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(e->hp_dev[i]) + off, static_cast<const char*>(src[i]) + off,
                                      size_t(cnt) * per_in[i] * e->esz, cudaMemcpyDefault, s));
+            dchunk[i] = static_cast<char*>(e->hp_dev[i]) + off;
         }
         char* dF = static_cast<char*>(e->hp_dev[4]) + size_t(b0) * 3 * e->esz;
         char* dT = static_cast<char*>(e->hp_dev[5]) + size_t(b0) * 3 * e->esz;
         char* dW = bpr ? static_cast<char*>(e->hp_dev[6]) + size_t(b0 / bpr) * 6 * e->esz : nullptr;
-        int rc = step_device(e, LAYOUT_SPLIT, static_cast<char*>(e->hp_dev[0]) + size_t(b0) * 3 * e->esz,
-                             static_cast<char*>(e->hp_dev[1]) + size_t(b0) * 4 * e->esz,
-                             static_cast<char*>(e->hp_dev[2]) + size_t(b0) * 3 * e->esz,
-                             static_cast<char*>(e->hp_dev[3]) + size_t(b0) * 3 * e->esz, dt, dF, dT, dW, cnt, b0,
+        int rc = step_device(e, layout, dchunk[0], dchunk[1], dchunk[2], dchunk[3], dt, dF, dT, dW, cnt, b0,
                              static_cast<char*>(e->prev) + size_t(b0) * 6 * e->esz, coeff_at(e, b0), s);
         if (rc) return rc;
         CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(dst[0]) + size_t(b0) * 3 * e->esz, dF, size_t(cnt) * 3 * e->esz,
@@ -1332,6 +1412,32 @@ int h2o_step_host(h2o_handle h, const void* pos, const void* quat, const void* l
         memcpy(out[i], dst[i], bytes);
     }
     return H2O_OK;
+}
+
+int h2o_step_host(h2o_handle h, const void* pos, const void* quat, const void* lin_vel, const void* ang_vel,
+                  double dt, void* out_force, void* out_torque, void* out_robot_wrench)
+{
+    h2o_engine* e = check(h);
+    if (!e) return H2O_ERR_BAD_HANDLE;
+    const void* in[4] = {pos, quat, lin_vel, ang_vel};
+    void* out[3] = {out_force, out_torque, out_robot_wrench};
+    return step_host_impl(e, LAYOUT_SPLIT, in, out, dt);
+}
+
+int h2o_step_host_physx(h2o_handle h, const void* transforms, const void* velocities, double dt, void* out_force,
+                        void* out_torque, void* out_robot_wrench)
+{
+    h2o_engine* e = check(h);
+    if (!e) return H2O_ERR_BAD_HANDLE;
+    const void* in[4] = {transforms, nullptr, velocities, nullptr};
+    void* out[3] = {out_force, out_torque, out_robot_wrench};
+    return step_host_impl(e, LAYOUT_PHYSX, in, out, dt);
+}
+
+int h2o_last_host_path(h2o_handle h)
+{
+    h2o_engine* e = check(h);
+    return e ? e->last_host_path : -1;
 }
 
 // ---- statistics / introspection ------------------------------------------------------------

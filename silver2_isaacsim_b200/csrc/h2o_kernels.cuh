@@ -78,6 +78,8 @@ struct StepArgs {
     // nullptr = equal runs of bodies_per_robot.  Wrenches then come from robot_wrench_kernel.
     const long long* robot_offsets;
     long long n_robots_var;
+    uint32_t* redo_bitmap;   // one bit per body of the ENGINE (index first_body + i), all zero between launches:
+                             // flagged bodies that found no slot in their CTA's deferred list
     int no_fallback;         // study knob H2O_NO_FALLBACK: 1 = keep the fast-path result of flagged bodies,
                              // k > 1 = re-evaluate exactly every k-th body instead (cost measurements)
 };
@@ -662,7 +664,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
         for (int s = 0; s < kStagesIn; ++s) mbar_init(&full_bar[s], 1);
         mbar_fence_init();
         fence_proxy_async_smem();
-        *redo_count = 0;
+        redo_count[0] = 0;  // deferred entries
+        redo_count[1] = 0;  // overflow in the current tile
     }
     pdl_wait_prerequisites();  // everything below reads / writes global memory
 
@@ -761,6 +764,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
 
         S F[3] = {S(0), S(0), S(0)}, T[3] = {S(0), S(0), S(0)};
         unsigned char* out = smem + SM::OFF_OUT + size_t(ostage) * SM::OUT_BYTES;
+        bool overflowed = false;  // flagged, but the CTA's list is full
         if (active) {
             if (kCopyOnly) {
                 // measurement aid (tile configs 10/11): same memory traffic, no arithmetic
@@ -787,13 +791,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
                             en.body = bi;
                             en.prev[0] = p0.x; en.prev[1] = p0.y; en.prev[2] = p1.x;
                             en.prev[3] = p1.y; en.prev[4] = p2.x; en.prev[5] = p2.y;
-                        } else {  // list full (thousands of flagged bodies per CTA): on the spot
-                            const ExactStepOut o = redo_exact<kLayout, kParam>(a, bi, env.surface_z);
-#pragma unroll
-                            for (int k = 0; k < 3; ++k) {
-                                F[k] = S(o.F[k]);
-                                T[k] = S(o.T[k]);
-                            }
+                        } else {  // list full (a workload that flags bodies wholesale): see below
+                            overflowed = true;
                         }
                     }
                 }
@@ -809,6 +808,17 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
             v.x = r.vx; v.y = r.vy; op[0] = v;
             v.x = r.vz; v.y = r.wx; op[1] = v;
             v.x = r.wy; v.y = r.wz; op[2] = v;
+            if (sizeof(S) == 4 && overflowed) {
+                // No slot in the deferred list: mark the body in the engine's bitmap and keep its OLD previous
+                // velocities in global memory (stage them instead of v), so that the sweep at the end of this
+                // CTA can re-evaluate it from global memory alone; it then writes the new row itself.  No call
+                // in here: a call inside the tile loop costs the hot path its registers (measured).
+                const long long gi = a.first_body + tile_begin + tid;
+                atomicOr(a.redo_bitmap + (gi >> 5), 1u << (gi & 31));
+                redo_count[1] = 1;
+                const V2* pr = reinterpret_cast<const V2*>(reinterpret_cast<const S*>(a.prev) + 6 * (tile_begin + tid));
+                op[0] = pr[0]; op[1] = pr[1]; op[2] = pr[2];
+            }
         }
         if (kRobot && active) {
             // torque of body i about the robot's slot-0 body: tau_i + (p_i - p_base) x F_i, parked in
@@ -821,7 +831,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
         }
         fence_proxy_async_smem();
         __syncthreads();  // (C) results (and robot accumulators) complete
-
         if (tid == 0) {
             const uint32_t cb = uint32_t(cnt) * sizeof(S);
             bulk_s2g(reinterpret_cast<S*>(a.out_force) + tile_begin * 3, out, cb * 3);
@@ -860,7 +869,29 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
     }
     if (sizeof(S) == 4 && !kCopyOnly) {
         __syncthreads();  // every tile done: the list is complete, every bulk store has been issued
-        const int n_redo = *redo_count < REDO_CAP ? *redo_count : REDO_CAP;
+        const int n_redo = redo_count[0] < REDO_CAP ? redo_count[0] : REDO_CAP;
+        const bool sweep = redo_count[1] != 0;
+        auto patch = [&](long long bi, const ExactStepOut& o) {  // replace a body's fast-path force / torque
+            float* of = reinterpret_cast<float*>(a.out_force) + 3 * bi;
+            float* ot = reinterpret_cast<float*>(a.out_torque) + 3 * bi;
+            if (kRobot) {
+                // the per-robot sums were formed from the fast-path values: add the difference
+                constexpr int EP = TL::E_POS;
+                const float* pos = reinterpret_cast<const float*>(a.pos);
+                const long long rb = bi / bpr;
+                const float* pb = pos + EP * (rb * bpr);
+                const float* pi = pos + EP * bi;
+                const float ax = pi[0] - pb[0], ay = pi[1] - pb[1], az = pi[2] - pb[2];
+                const float dfx = o.F[0] - of[0], dfy = o.F[1] - of[1], dfz = o.F[2] - of[2];
+                float* ow = reinterpret_cast<float*>(a.out_wrench) + rb * 6;
+                atomicAdd(ow + 0, dfx); atomicAdd(ow + 1, dfy); atomicAdd(ow + 2, dfz);
+                atomicAdd(ow + 3, (o.T[0] - ot[0]) + (ay * dfz - az * dfy));
+                atomicAdd(ow + 4, (o.T[1] - ot[1]) + (az * dfx - ax * dfz));
+                atomicAdd(ow + 5, (o.T[2] - ot[2]) + (ax * dfy - ay * dfx));
+            }
+            of[0] = o.F[0]; of[1] = o.F[1]; of[2] = o.F[2];
+            ot[0] = o.T[0]; ot[1] = o.T[1]; ot[2] = o.T[2];
+        };
         if (n_redo > 0) {  // CTA-uniform
             // scratch = the input stage (no load is in flight any more): [entry][role][ROLE_DOUBLES] doubles
             double* const scratch = reinterpret_cast<double*>(smem + SM::OFF_IN);
@@ -873,36 +904,35 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
                                                scratch + (lane * N_ROLES + role) * ROLE_DOUBLES);
             __syncthreads();
             ExactStepOut o;
-            long long bi = 0;
-            if (tid < n_redo) {
-                bi = redo_list[tid].body;
-                o = combine_roles(scratch + tid * N_ROLES * ROLE_DOUBLES);
-            }
+            if (tid < n_redo) o = combine_roles(scratch + tid * N_ROLES * ROLE_DOUBLES);
             if (tid == 0) bulk_wait_all<0>();  // the fast-path values of these bodies have landed ...
             __syncthreads();
-            if (tid < n_redo) {                // ... and are replaced
-                float* of = reinterpret_cast<float*>(a.out_force) + 3 * bi;
-                float* ot = reinterpret_cast<float*>(a.out_torque) + 3 * bi;
-                if (kRobot) {
-                    // the per-robot sums were formed from the fast-path values: add the difference
-                    constexpr int EP = TL::E_POS;
-                    const float* pos = reinterpret_cast<const float*>(a.pos);
-                    const long long rb = bi / bpr;
-                    const float* pb = pos + EP * (rb * bpr);
-                    const float* pi = pos + EP * bi;
-                    const float ax = pi[0] - pb[0], ay = pi[1] - pb[1], az = pi[2] - pb[2];
-                    const float dfx = o.F[0] - of[0], dfy = o.F[1] - of[1], dfz = o.F[2] - of[2];
-                    float* ow = reinterpret_cast<float*>(a.out_wrench) + rb * 6;
-                    atomicAdd(ow + 0, dfx); atomicAdd(ow + 1, dfy); atomicAdd(ow + 2, dfz);
-                    atomicAdd(ow + 3, (o.T[0] - ot[0]) + (ay * dfz - az * dfy));
-                    atomicAdd(ow + 4, (o.T[1] - ot[1]) + (az * dfx - ax * dfz));
-                    atomicAdd(ow + 5, (o.T[2] - ot[2]) + (ax * dfy - ay * dfx));
+            if (tid < n_redo) patch(redo_list[tid].body, o);  // ... and are replaced
+        } else {
+            if (tid == 0) bulk_wait_all<0>();
+            if (sweep) __syncthreads();
+        }
+        if (sweep) {
+            // The list overflowed in some tile: sweep this CTA's tiles for marked bodies.  Their previous
+            // velocities in global memory are still the old ones; after the float64 evaluation the thread
+            // writes force, torque and the new row, and clears the mark (the bitmap is all zero again).
+            for (int it = 0; it < n_it; ++it) {
+                const long long bi = tile_start(it) + tid;
+                const long long gi = a.first_body + bi;
+                if (tid < TB && ((a.redo_bitmap[gi >> 5] >> (gi & 31)) & 1u)) {
+                    const ExactStepOut o = redo_exact<kLayout, kParam>(a, bi, env.surface_z);
+                    patch(bi, o);
+                    BodyPtrs<float> bp;
+                    bp.pos = reinterpret_cast<const float*>(a.pos); bp.quat = reinterpret_cast<const float*>(a.quat);
+                    bp.lin = reinterpret_cast<const float*>(a.lin); bp.ang = reinterpret_cast<const float*>(a.ang);
+                    bp.prev = reinterpret_cast<const float*>(a.prev); bp.coeff = nullptr;
+                    RawBody<float> rr;
+                    load_raw<float, kLayout>(bp, bi, rr);
+                    float* pv = reinterpret_cast<float*>(a.prev) + 6 * bi;
+                    pv[0] = rr.vx; pv[1] = rr.vy; pv[2] = rr.vz; pv[3] = rr.wx; pv[4] = rr.wy; pv[5] = rr.wz;
+                    atomicAnd(a.redo_bitmap + (gi >> 5), ~(1u << (gi & 31)));
                 }
-                of[0] = o.F[0]; of[1] = o.F[1]; of[2] = o.F[2];
-                ot[0] = o.T[0]; ot[1] = o.T[1]; ot[2] = o.T[2];
             }
-        } else if (tid == 0) {
-            bulk_wait_all<0>();
         }
     } else if (tid == 0) {
         bulk_wait_all<0>();

@@ -644,10 +644,17 @@ H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], boo
     // d = R^T v_hat carried in H: when the flow is nearly parallel to a face, d_j is a cancelled sum of O(1)
     // products and the centre of pressure is a RATIO of such alignments; L products of an L-rounded R lose
     // it (1e-5 relative on the drag lever arm for alignments ~1e-3).  All nine H entries of R exist already.
+#if defined(H2O_D_IN_L)  // cost experiment only: the round-1 fp32 alignment
+    const L ux_ = in.vx * inv_speed, uy_ = in.vy * inv_speed, uz_ = in.vz * inv_speed;
+    const L d0 = r00 * ux_ + r10 * uy_ + r20 * uz_;
+    const L d1 = r01 * ux_ + r11 * uy_ + r21 * uz_;
+    const L d2 = r02 * ux_ + r12 * uy_ + r22 * uz_;
+#else
     const H vxh = H(in.vx), vyh = H(in.vy), vzh = H(in.vz);
     const L d0 = L((H(1) - (hyy + hzz)) * vxh + (hxy + hwz) * vyh + r20h * vzh) * inv_speed;
     const L d1 = L((hxy - hwz) * vxh + (H(1) - (hxx + hzz)) * vyh + r21h * vzh) * inv_speed;
     const L d2 = L((hxz + hwy) * vxh + (hyz - hwx) * vyh + r22h * vzh) * inv_speed;
+#endif
 
     // ---- projected area, centre of pressure (body frame) -- see body_terms
     const uint32_t f0 = (d0 < L(0)) ? (1u << kp_bit(1, 0, 0)) : (1u << kp_bit(-1, 0, 0));
@@ -757,7 +764,11 @@ H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], boo
         // (b): buoyancy is the only force group that does not vanish with the velocities, so a cancelled net
         // force means |F| << F_buoyancy
         flag_kt = t1 / h2o_max(mt, L(1e-30)); flag_kf = f1 / h2o_max(L(fbz), L(1e-30));
+#if defined(H2O_NO_FLAGS)  // cost experiment only: no conditioning check (the dq check stays)
+        suspect = h2o_abs(dqh) > H(FAST_PATH_MAX_DQ);
+#else
         suspect = (t1 < L(FLAG_KAPPA_T) * mt) | (f1 < L(FLAG_KAPPA_F) * L(fbz)) | (h2o_abs(dqh) > H(FAST_PATH_MAX_DQ));
+#endif
     }
 
     if (diag) {  // precision study only (tests/harness/precision_study.py): magnitudes of the term groups

@@ -244,6 +244,11 @@ class HydroEngine:
         """``components`` reproduces the deviations of the reference's Warp twin."""
         L.check(self._lib.h2o_set_warp_compat(self._h, int(bool(enable))))
 
+    def set_strict(self, enable: bool = True):
+        """fp32 mode: ``True`` (default) guarantees the parity bound for every body (bodies whose force / torque
+        groups cancel are re-evaluated in float64); ``False`` keeps the plain fp32 result for them."""
+        L.check(self._lib.h2o_set_strict(self._h, int(bool(enable))))
+
     def set_tile_config(self, cfg: int = 0):
         """Tuning knob: tile-kernel variant (0 = default)."""
         L.check(self._lib.h2o_set_tile_config(self._h, int(cfg)))
@@ -404,38 +409,57 @@ class HydroEngine:
         return res + (flags,) if return_flags else res
 
     # ------------------------------------------------------------------ host arrays
+    def _host_in(self, x, cols):
+        npdt = _NP_DTYPES[_TORCH_DTYPES[self.dtype]]
+        if isinstance(x, torch.Tensor):
+            if x.is_cuda or x.dtype != self.dtype or not x.is_contiguous():
+                raise ValueError("step_host takes contiguous CPU tensors of the engine dtype")
+            assert tuple(x.shape) == (self.n_bodies, cols)
+            return x, x.data_ptr()
+        a = np.ascontiguousarray(x, dtype=npdt)
+        assert a.shape == (self.n_bodies, cols), (a.shape, cols)
+        return a, a.ctypes.data
+
+    def _host_out(self, x, rows, cols):
+        npdt = _NP_DTYPES[_TORCH_DTYPES[self.dtype]]
+        if x is None:
+            x = np.empty((rows, cols), dtype=npdt)
+        if isinstance(x, torch.Tensor):
+            return x, x.data_ptr()
+        assert x.dtype == npdt and x.flags.c_contiguous and x.shape == (rows, cols)
+        return x, x.ctypes.data
+
     def step_host(self, position, orientation_quat, linear_vel, angular_vel, dt: float, out_force=None,
                   out_torque=None, out_robot_wrench=None, robot_wrench: bool = False):
-        """NumPy / pinned-CPU-tensor in, same out (chunked H2D -> kernel -> D2H pipeline)."""
-        npdt = _NP_DTYPES[_TORCH_DTYPES[self.dtype]]
-
-        def host(x, cols):
-            if isinstance(x, torch.Tensor):
-                if x.is_cuda or x.dtype != self.dtype or not x.is_contiguous():
-                    raise ValueError("step_host takes contiguous CPU tensors of the engine dtype")
-                assert tuple(x.shape) == (self.n_bodies, cols)
-                return x, x.data_ptr()
-            a = np.ascontiguousarray(x, dtype=npdt)
-            assert a.shape == (self.n_bodies, cols), (a.shape, cols)
-            return a, a.ctypes.data
-
-        def host_out(x, rows, cols):
-            if x is None:
-                x = np.empty((rows, cols), dtype=npdt)
-            if isinstance(x, torch.Tensor):
-                return x, x.data_ptr()
-            assert x.dtype == npdt and x.flags.c_contiguous and x.shape == (rows, cols)
-            return x, x.ctypes.data
-
-        keep = [host(position, 3), host(orientation_quat, 4), host(linear_vel, 3), host(angular_vel, 3)]
-        F, pf = host_out(out_force, self.n_bodies, 3)
-        T, pt = host_out(out_torque, self.n_bodies, 3)
+        """NumPy / CPU-tensor in, same out.  Pinned (page-locked) buffers take the zero-copy path: the fused
+        kernel reads and writes them over PCIe directly (TMA bulk copies), no staging; pageable buffers go
+        through a chunked H2D -> kernel -> D2H pipeline.  ``last_host_path`` tells which."""
+        keep = [self._host_in(position, 3), self._host_in(orientation_quat, 4), self._host_in(linear_vel, 3),
+                self._host_in(angular_vel, 3)]
+        F, pf = self._host_out(out_force, self.n_bodies, 3)
+        T, pt = self._host_out(out_torque, self.n_bodies, 3)
         W, pw = (None, None)
         if robot_wrench or out_robot_wrench is not None:
-            W, pw = host_out(out_robot_wrench, self.n_bodies // self.bodies_per_robot, 6)
+            W, pw = self._host_out(out_robot_wrench, self.n_bodies // self.bodies_per_robot, 6)
         L.check(self._lib.h2o_step_host(self._h, keep[0][1], keep[1][1], keep[2][1], keep[3][1], float(dt),
                                         pf, pt, pw))
         return (F, T) if W is None else (F, T, W)
+
+    def step_host_physx(self, transforms, velocities, dt: float, out_force=None, out_torque=None,
+                        out_robot_wrench=None, robot_wrench: bool = False):
+        """Same with the PhysX layout on the host: transforms (N,7) = [p, q], velocities (N,6) = [v, w]."""
+        keep = [self._host_in(transforms, 7), self._host_in(velocities, 6)]
+        F, pf = self._host_out(out_force, self.n_bodies, 3)
+        T, pt = self._host_out(out_torque, self.n_bodies, 3)
+        W, pw = (None, None)
+        if robot_wrench or out_robot_wrench is not None:
+            W, pw = self._host_out(out_robot_wrench, self.n_bodies // self.bodies_per_robot, 6)
+        L.check(self._lib.h2o_step_host_physx(self._h, keep[0][1], keep[1][1], float(dt), pf, pt, pw))
+        return (F, T) if W is None else (F, T, W)
+
+    @property
+    def last_host_path(self) -> str:
+        return {1: "zero-copy", 2: "staged"}.get(int(self._lib.h2o_last_host_path(self._h)), "none")
 
     # ------------------------------------------------------------------ introspection
     def stats(self, reset: bool = False) -> dict:

@@ -536,8 +536,21 @@ def test_step_host_pipeline(oracle, dev):
     e3 = _engine(wl, torch.float32, dev)
     e3.set_prev(_t(wl.prev_lin, torch.float32, dev), _t(wl.prev_ang, torch.float32, dev))
     e3.step_host(*pin, wl.dt, out_force=oF, out_torque=oT)
+    assert e.last_host_path == "staged" and e3.last_host_path == "zero-copy"  # NumPy arrays vs pinned tensors
     for x, y in ((oF.numpy(), F), (oT.numpy(), T)):  # different chunking (no robot tiles) -> rounding-level
         assert scoring.fp32_ok(x, y, rel=2e-6).mean() > 0.999 and scoring.fp32_ok(x, y, rel=1e-4).all()
+    _check(wl, torch.float32, ref, oF.numpy().astype(np.float64), oT.numpy().astype(np.float64), "step_host zero-copy")
+    # PhysX layout on the host (two input arrays), pinned and pageable, with the robot wrench
+    for pinned in (True, False):
+        e4 = _engine(wl, torch.float32, dev)
+        e4.set_prev(_t(wl.prev_lin, torch.float32, dev), _t(wl.prev_ang, torch.float32, dev))
+        tr, ve = wl.transforms(), wl.velocities()
+        if pinned:
+            tr, ve = torch.as_tensor(tr).pin_memory(), torch.as_tensor(ve).pin_memory()
+        F4, T4, W4 = e4.step_host_physx(tr, ve, wl.dt, robot_wrench=True)
+        assert e4.last_host_path == ("zero-copy" if pinned else "staged")
+        _check(wl, torch.float32, ref, np.asarray(F4, dtype=np.float64), np.asarray(T4, dtype=np.float64), "step_host_physx")
+        np.testing.assert_allclose(np.asarray(W4), W2, rtol=1e-5, atol=1e-4)
 
 
 def test_step_host_table_slots_and_height_field(oracle, dev):
