@@ -854,7 +854,12 @@ def run_b200(args):
                "value_p10": total_bodies * e2e_steps / (pctl(ms_e2e, 90) * 1e-3),
                "value_p90": total_bodies * e2e_steps / (pctl(ms_e2e, 10) * 1e-3),
                "host_clock_value": total_bodies * e2e_steps / e2e_wall,
-               "api": "HydroEngine.step_host (h2o_step_host): pinned host buffers in/out, chunked multi-stream pipeline"}
+               "api": "HydroEngine.step_host (h2o_step_host), pinned host buffers in and out",
+               "path": eng.last_host_path,
+               "note": "zero-copy: the fused tile kernel runs on the pinned host buffers (TMA bulk loads pull the 13 input "
+                       "scalars per body over PCIe, bulk stores push the 6 output scalars back); one kernel per step, "
+                       "transfers and arithmetic overlap tile by tile" if eng.last_host_path == "zero-copy" else
+                       "staged: chunked H2D -> kernel -> D2H pipeline on three streams"}
         try:
             e2e["platform_ceiling"] = platform_ceiling(torch, sharding, n, esz, dev)
             e2e["frac_of_ceiling"] = e2e["value"] / e2e["platform_ceiling"]["value"]

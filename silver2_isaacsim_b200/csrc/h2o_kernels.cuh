@@ -81,7 +81,7 @@ struct StepArgs {
     uint32_t* redo_bitmap;   // one bit per body of the ENGINE (index first_body + i), all zero between launches:
                              // flagged bodies that found no slot in their CTA's deferred list
     int no_fallback;         // study knob H2O_NO_FALLBACK: 1 = keep the fast-path result of flagged bodies,
-                             // k > 1 = re-evaluate exactly every k-th body instead (cost measurements)
+                             // k = 2^j > 1 = re-evaluate exactly every k-th body instead (cost measurements)
 };
 
 // ---------------------------------------------------------------------------
@@ -373,7 +373,7 @@ template <int kRole, int kLayout, int kParam>
 __device__ __noinline__ void exact_role_from_global(
     const float* pos, const float* quat, const float* lin, const float* ang, const float* prev_row, const float* coeff,
     const int32_t* slot_type, long long i, long long first_body, int n_slots, int quat_wxyz, double rho, double grav,
-    double inv_dt, double surface_z, float cx, float cy, float cz, double* out)
+    double inv_dt, double surface_z, float cx, float cy, float cz, uint32_t kp_mask, double* out)
 {
     BodyPtrs<float> bp;
     bp.pos = pos; bp.quat = quat; bp.lin = lin; bp.ang = ang; bp.prev = prev_row; bp.coeff = coeff;
@@ -398,7 +398,7 @@ __device__ __noinline__ void exact_role_from_global(
     g.rho_h = rho; g.grav_h = grav; g.rho = double(float(rho));
     g.am_dense = nullptr;
     Terms<double, double> t;
-    body_terms<double, double, false>(g, t);
+    body_terms<double, double, false>(g, t, &kp_mask);
     if (kRole == ROLE_DRAG) {
         out[0] = t.fd[0]; out[1] = t.fd[1]; out[2] = t.fd[2];
         out[3] = t.tarm[0]; out[4] = t.tarm[1]; out[5] = t.tarm[2];
@@ -416,14 +416,14 @@ __device__ __noinline__ void exact_role_from_global(
 }
 template <int kLayout, int kParam>
 __device__ __forceinline__ void redo_role(int role, const StepArgs& a, long long i, double surface_z, const float* prev_row,
-                                          double* out)
+                                          uint32_t kp_mask, double* out)
 {
 #define H2O_ROLE(R)                                                                                                        \
     exact_role_from_global<R, kLayout, kParam>(                                                                            \
         reinterpret_cast<const float*>(a.pos), reinterpret_cast<const float*>(a.quat), reinterpret_cast<const float*>(a.lin), \
         reinterpret_cast<const float*>(a.ang), prev_row, reinterpret_cast<const float*>(a.coeff), a.slot_type, i,         \
         a.first_body, a.n_slots, a.quat_wxyz, a.rho, a.grav, a.inv_dt, surface_z, float(a.current[0]), float(a.current[1]), \
-        float(a.current[2]), out)
+        float(a.current[2]), kp_mask, out)
     if (role == ROLE_DRAG) H2O_ROLE(ROLE_DRAG);
     else if (role == ROLE_LIFT) H2O_ROLE(ROLE_LIFT);
     else if (role == ROLE_HYDROSTATIC) H2O_ROLE(ROLE_HYDROSTATIC);
@@ -462,13 +462,14 @@ __device__ __noinline__ ExactStepOut combine_roles(const double* p)
 // fp64 mode: the world-frame formulation (exact in dq).
 template <typename S>
 __device__ __forceinline__ bool body_step(const BodyIn<double, S>& in, S mass, S F[3], S T[3], bool& clamped,
-                                          bool& still, double& ratio)
+                                          bool& still, double& ratio, uint32_t& mask)
 {
     if (sizeof(S) == 4) {
         bool suspect;
-        body_wrench_fast<double, S>(in, mass, F, T, clamped, ratio, still, suspect);
+        body_wrench_fast<double, S>(in, mass, F, T, clamped, ratio, still, suspect, mask);
         return suspect;
     } else {
+        mask = 0;
         Terms<double, S> t;
         body_terms<double, S, false>(in, t);
         net_wrench<double, S>(t, mass, F, T, clamped);
@@ -500,14 +501,14 @@ __device__ __forceinline__ void accumulate_stats(ThreadStats& st, double fx, dou
 // `i` = body index inside the launch (a.pos etc. are the launch's base pointers).
 template <typename S, int kLayout, int kParam, bool kStats, bool kDefer>
 __device__ __forceinline__ bool step_one_body(const StepArgs& a, long long i, const BodyIn<double, S>& in, S mass,
-                                              double surface_z, S F[3], S T[3], ThreadStats& st)
+                                              double surface_z, S F[3], S T[3], ThreadStats& st, uint32_t& mask)
 {
     bool clamped, still;
     double ratio;
-    bool redo = body_step<S>(in, mass, F, T, clamped, still, ratio);
+    bool redo = body_step<S>(in, mass, F, T, clamped, still, ratio, mask);
     if (sizeof(S) == 4) {
         redo = redo && a.no_fallback != 1;
-        if (a.no_fallback > 1) redo = ((a.first_body + i) % a.no_fallback) == 0;  // study knob: every k-th body
+        if (a.no_fallback > 1) redo = ((a.first_body + i) & (long long)(a.no_fallback - 1)) == 0;  // study knob: every k-th body, k = 2^j
         if (redo && !kDefer) {
             const ExactStepOut o = redo_exact<kLayout, kParam>(a, i, surface_z);
 #pragma unroll
@@ -583,6 +584,8 @@ template <typename S, int kLayout, int kParam> struct TileLayout {
 struct RedoEntry {
     long long body;   // index inside the launch
     float prev[6];    // previous [v, w] as they were before this step
+    uint32_t mask;    // submerged-keypoint mask of the fast path (the same H compares body_terms would repeat)
+    uint32_t pad_;
 };
 constexpr int REDO_CAP = 24;  // 24 bodies x 4 roles x 10 doubles of scratch fit the smallest input stage
 
@@ -773,7 +776,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
             } else {
                 BodyIn<double, S> bin;
                 make_body_in<S>(r, cl, a.quat_wxyz, a.rho, a.grav, inv_dt, env, bin);
-                if (step_one_body<S, kLayout, kParam, kStats, true>(a, tile_begin + tid, bin, cl[10], env.surface_z, F, T, st)) {
+                uint32_t kp_mask;
+                if (step_one_body<S, kLayout, kParam, kStats, true>(a, tile_begin + tid, bin, cl[10], env.surface_z, F, T, st, kp_mask)) {
                     if (sizeof(S) == 4) {
                         const long long bi = tile_begin + tid;
                         const int slot = atomicAdd(redo_count, 1);
@@ -789,6 +793,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
                             if (TL::E_COEFF) prefetch_l2_keep(reinterpret_cast<const S*>(a.coeff) + TL::E_COEFF * bi);
                             RedoEntry& en = redo_list[slot];
                             en.body = bi;
+                            en.mask = kp_mask;
                             en.prev[0] = p0.x; en.prev[1] = p0.y; en.prev[2] = p1.x;
                             en.prev[3] = p1.y; en.prev[4] = p2.x; en.prev[5] = p2.y;
                         } else {  // list full (a workload that flags bodies wholesale): see below
@@ -901,7 +906,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
             for (int role = warp; role < N_ROLES; role += n_warps)
                 if (lane < n_redo)
                     redo_role<kLayout, kParam>(role, a, redo_list[lane].body, env.surface_z, redo_list[lane].prev,
-                                               scratch + (lane * N_ROLES + role) * ROLE_DOUBLES);
+                                               redo_list[lane].mask, scratch + (lane * N_ROLES + role) * ROLE_DOUBLES);
             __syncthreads();
             ExactStepOut o;
             if (tid < n_redo) o = combine_roles(scratch + tid * N_ROLES * ROLE_DOUBLES);
@@ -987,7 +992,8 @@ __global__ void __launch_bounds__(256) step_direct_kernel(const __grid_constant_
         if (a.am_dense)
             bin.am_dense = reinterpret_cast<const S*>(a.am_dense) + 36 * a.am_slot_type[(a.first_body + i) % a.am_n_slots];
         S F[3], T[3];
-        step_one_body<S, kLayout, kParam, kStats, false>(a, i, bin, cl[10], env.surface_z, F, T, st);
+        uint32_t kp_mask;
+        step_one_body<S, kLayout, kParam, kStats, false>(a, i, bin, cl[10], env.surface_z, F, T, st, kp_mask);
         S* of = reinterpret_cast<S*>(a.out_force) + 3 * i;
         S* ot = reinterpret_cast<S*>(a.out_torque) + 3 * i;
         of[0] = F[0]; of[1] = F[1]; of[2] = F[2];
@@ -1294,7 +1300,8 @@ __global__ void rollout_persistent_kernel(const __grid_constant__ RolloutArgs a)
             make_body_in<S>(r, cl, a.quat_wxyz, a.rho, a.grav, inv_dt, env, bin);
             bool clamped, still;
             double ratio;
-            bool redo = body_step<S>(bin, cl[10], F, T, clamped, still, ratio);
+            uint32_t kp_mask;
+            bool redo = body_step<S>(bin, cl[10], F, T, clamped, still, ratio, kp_mask);
             if (sizeof(S) == 4) {
                 redo = redo && a.no_fallback != 1;
                 if (redo) {

@@ -289,37 +289,40 @@ template <typename H> struct Waterline {
     H ratio;         // submersion ratio after the 1e-9 cut (numba_hydrodynamics.py:87, :277-279)
     bool partial;    // z_min < 0 < z_max: the centre of buoyancy is the mean of the wet keypoints
 };
-template <typename H>
+// kMask = false: the caller already holds the mask (w.mask is left alone); only the ratio is formed
+template <typename H, bool kMask = true>
 H2O_HD void waterline(H pz, H r20h, H r21h, H r22h, H dxh, H dyh, H dzh, Waterline<H>& w)
 {
     const H a = r20h * (dxh * H(0.5));
     const H b = r21h * (dyh * H(0.5));
     const H c = r22h * (dzh * H(0.5));
-    const H abp = a + b, abm = a - b;
-    const H m = -pz;  // keypoint wet  <=>  fl(t + pz) < 0  <=>  t < -pz  (exact)
-    uint32_t mask = 0;
+    if (kMask) {
+        const H abp = a + b, abm = a - b;
+        const H m = -pz;  // keypoint wet  <=>  fl(t + pz) < 0  <=>  t < -pz  (exact)
+        uint32_t mask = 0;
 #define H2O_KP(i, j, k, tval)                                                   \
     {                                                                           \
         const H tv = (tval);                                                    \
         h2o_or_if_less(mask, tv, m, 1u << kp_bit(i, j, k));                     \
         h2o_or_if_less(mask, -tv, m, 1u << kp_bit(-(i), -(j), -(k)));           \
     }
-    H2O_KP(1, 0, 0, a)
-    H2O_KP(0, 1, 0, b)
-    H2O_KP(1, 1, 0, abp)
-    H2O_KP(1, -1, 0, abm)
-    H2O_KP(0, 0, 1, c)
-    H2O_KP(1, 0, 1, a + c)
-    H2O_KP(1, 0, -1, a - c)
-    H2O_KP(0, 1, 1, b + c)
-    H2O_KP(0, 1, -1, b - c)
-    H2O_KP(1, 1, 1, abp + c)
-    H2O_KP(1, 1, -1, abp - c)
-    H2O_KP(1, -1, 1, abm + c)
-    H2O_KP(1, -1, -1, abm - c)
+        H2O_KP(1, 0, 0, a)
+        H2O_KP(0, 1, 0, b)
+        H2O_KP(1, 1, 0, abp)
+        H2O_KP(1, -1, 0, abm)
+        H2O_KP(0, 0, 1, c)
+        H2O_KP(1, 0, 1, a + c)
+        H2O_KP(1, 0, -1, a - c)
+        H2O_KP(0, 1, 1, b + c)
+        H2O_KP(0, 1, -1, b - c)
+        H2O_KP(1, 1, 1, abp + c)
+        H2O_KP(1, 1, -1, abp - c)
+        H2O_KP(1, -1, 1, abm + c)
+        H2O_KP(1, -1, -1, abm - c)
 #undef H2O_KP
-    h2o_or_if_less(mask, H(0), m, 1u << kp_bit(0, 0, 0));
-
+        h2o_or_if_less(mask, H(0), m, 1u << kp_bit(0, 0, 0));
+        w.mask = mask;
+    }
     const H ext = (h2o_abs(a) + h2o_abs(b)) + h2o_abs(c);  // highest keypoint above p
     const H z_min = pz - ext, z_max = pz + ext;
     const bool dry = z_min >= H(0);
@@ -328,14 +331,13 @@ H2O_HD void waterline(H pz, H r20h, H r21h, H r22h, H dxh, H dyh, H dzh, Waterli
     H ratio = H(1);
     if (partial && !(total_height < H(1e-6))) ratio = h2o_min(H(1), -z_min * h2o_rcp_h(total_height));
     if (dry || !(ratio > H(1e-9))) ratio = H(0);  // numba_hydrodynamics.py:87, :277-279
-    w.mask = mask;
     w.ratio = ratio;
     w.partial = partial;
 }
 
 // One body, branch-free.  kExactTrig: asin/sin as the reference vs 2d*sqrt(1-d^2).
 template <typename H, typename L, bool kExactTrig>
-H2O_HD void body_terms(const BodyIn<H, L>& in, Terms<H, L>& t, const Waterline<H>* given = nullptr)
+H2O_HD void body_terms(const BodyIn<H, L>& in, Terms<H, L>& t, const uint32_t* given_mask = nullptr)
 {
     // ---- rotation (numba_hydrodynamics.py:14-49).  Row 2 in H for the waterline.
     const H hx2 = in.qx + in.qx, hy2 = in.qy + in.qy, hz2 = in.qz + in.qz;
@@ -347,8 +349,12 @@ H2O_HD void body_terms(const BodyIn<H, L>& in, Terms<H, L>& t, const Waterline<H
 
     const H dxh = H(in.dimx), dyh = H(in.dimy), dzh = H(in.dimz);
     Waterline<H> wl;
-    if (given) wl = *given;  // a caller that has run the identical H arithmetic already (body_wrench_fast)
-    else waterline<H>(in.pz, r20h, r21h, r22h, dxh, dyh, dzh, wl);
+    if (given_mask) {  // a caller that has run the identical 27 H compares already (body_wrench_fast)
+        wl.mask = *given_mask;
+        waterline<H, false>(in.pz, r20h, r21h, r22h, dxh, dyh, dzh, wl);
+    } else {
+        waterline<H>(in.pz, r20h, r21h, r22h, dxh, dyh, dzh, wl);
+    }
     const uint32_t mask = wl.mask;
     const H ratio = wl.ratio;
     const bool partial = wl.partial;
@@ -576,7 +582,7 @@ H2O_HD void net_wrench(const Terms<H, L>& t, L mass, L F[3], L T[3], bool& clamp
 // ---------------------------------------------------------------------------
 template <typename H, typename L>
 H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], bool& clamped, H& ratio_out,
-                             bool& still, bool& suspect, L* diag = nullptr)
+                             bool& still, bool& suspect, uint32_t& mask_out, L* diag = nullptr)
 {
     // ---- waterline in H (the same function body_terms calls)
     const H hx2 = in.qx + in.qx, hy2 = in.qy + in.qy, hz2 = in.qz + in.qz;
@@ -593,6 +599,7 @@ H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], boo
     const uint32_t mask = wl.mask;
     const H ratio = wl.ratio;
     const bool partial = wl.partial;
+    mask_out = mask;
     ratio_out = ratio;
     const L rl = L(ratio);
     const H fbz = in.rho_h * (ratio * (dxh * dyh * dzh)) * in.grav_h;  // numba_hydrodynamics.py:282

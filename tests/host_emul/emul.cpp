@@ -59,7 +59,8 @@ static void run(int64_t n, const double* pos, const double* quat, const double* 
             H ratio;
             bool still, suspect;
             L dg[14] = {0};
-            body_wrench_fast<H, L>(in, L(S(c[10])), f, tq, clamped, ratio, still, suspect, comp ? dg : nullptr);
+            uint32_t kp_mask;
+            body_wrench_fast<H, L>(in, L(S(c[10])), f, tq, clamped, ratio, still, suspect, kp_mask, comp ? dg : nullptr);
             if (comp) {  // mode 4 returns the term-group magnitudes where the other modes return components
                 for (int k = 0; k < 14; ++k) comp[28 * i + k] = double(dg[k]);
                 comp[28 * i + 27] = suspect ? 2.0 : 1.0;
@@ -89,7 +90,7 @@ static void run(int64_t n, const double* pos, const double* quat, const double* 
                 }
                 Terms<double, double> te;
                 double fe[3], qe[3];
-                body_terms<double, double, false>(ex, te);
+                body_terms<double, double, false>(ex, te, &kp_mask);  // as the tile kernel's deferred roles do
                 net_wrench<double, double>(te, double(S(c[10])), fe, qe, clamped);
                 for (int k = 0; k < 3; ++k) { f[k] = L(fe[k]); tq[k] = L(qe[k]); }
             }

@@ -545,9 +545,12 @@ def test_step_host_pipeline(oracle, dev):
         e4 = _engine(wl, torch.float32, dev)
         e4.set_prev(_t(wl.prev_lin, torch.float32, dev), _t(wl.prev_ang, torch.float32, dev))
         tr, ve = wl.transforms(), wl.velocities()
-        if pinned:
+        outs = {}
+        if pinned:  # zero-copy needs every buffer page-locked, outputs included
             tr, ve = torch.as_tensor(tr).pin_memory(), torch.as_tensor(ve).pin_memory()
-        F4, T4, W4 = e4.step_host_physx(tr, ve, wl.dt, robot_wrench=True)
+            outs = dict(out_force=torch.empty(wl.n, 3).pin_memory(), out_torque=torch.empty(wl.n, 3).pin_memory(),
+                        out_robot_wrench=torch.empty(wl.n // 19, 6).pin_memory())
+        F4, T4, W4 = e4.step_host_physx(tr, ve, wl.dt, robot_wrench=True, **outs)
         assert e4.last_host_path == ("zero-copy" if pinned else "staged")
         _check(wl, torch.float32, ref, np.asarray(F4, dtype=np.float64), np.asarray(T4, dtype=np.float64), "step_host_physx")
         np.testing.assert_allclose(np.asarray(W4), W2, rtol=1e-5, atol=1e-4)
