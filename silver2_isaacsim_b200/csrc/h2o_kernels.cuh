@@ -914,7 +914,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
             __syncthreads();
             if (tid < n_redo) patch(redo_list[tid].body, o);  // ... and are replaced
         } else {
-            if (tid == 0) bulk_wait_all<0>();
+            // Nothing to patch: the CTA may retire as soon as the bulk stores have READ their shared-memory
+            // source (the writes drain on their own; grid completion orders them before the next kernel) --
+            // ~0.5 us less tail than waiting for the writes themselves.
+            if (tid == 0) {
+                if (sweep) bulk_wait_all<0>();
+                else bulk_wait_read<0>();
+            }
             if (sweep) __syncthreads();
         }
         if (sweep) {
@@ -940,7 +946,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
             }
         }
     } else if (tid == 0) {
-        bulk_wait_all<0>();
+        bulk_wait_read<0>();
     }
     if (kStats && a.stats) flush_stats(st, a.stats);
 }

@@ -754,8 +754,10 @@ H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], boo
 
     F[0] = (r00 * ffx + r01 * ffy + r02 * ffz) - (gam * in.vx + ml * in.ax);
     F[1] = (r10 * ffx + r11 * ffy + r12 * ffz) - (gam * in.vy + ml * in.ay);
-    const L fz = (r20 * ffx + r21 * ffy + r22 * ffz) - (gam * in.vz + ml * in.az);
-    F[2] = L(fbz + H(fz));
+    // buoyancy joins in L: its rounding (6e-8 fbz) reaches the bound only where |F| < 0.6 % of fbz, and those
+    // bodies are flagged below (|F| < FLAG_KAPPA_F fbz)
+    const L fbl = L(fbz);
+    F[2] = fbl + ((r20 * ffx + r21 * ffy + r22 * ffz) - (gam * in.vz + ml * in.az));
 
     // ---- conditioning check.  L arithmetic carries ~1e-7 relative error per TERM; the result meets the
     // fp32-mode bound (1e-5 relative per vector) unless that error is amplified:
@@ -770,11 +772,11 @@ H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], boo
         const L f1 = (h2o_abs(F[0]) + h2o_abs(F[1])) + h2o_abs(F[2]);
         // (b): buoyancy is the only force group that does not vanish with the velocities, so a cancelled net
         // force means |F| << F_buoyancy
-        flag_kt = t1 / h2o_max(mt, L(1e-30)); flag_kf = f1 / h2o_max(L(fbz), L(1e-30));
+        flag_kt = t1 / h2o_max(mt, L(1e-30)); flag_kf = f1 / h2o_max(fbl, L(1e-30));
 #if defined(H2O_NO_FLAGS)  // cost experiment only: no conditioning check (the dq check stays)
         suspect = h2o_abs(dqh) > H(FAST_PATH_MAX_DQ);
 #else
-        suspect = (t1 < L(FLAG_KAPPA_T) * mt) | (f1 < L(FLAG_KAPPA_F) * L(fbz)) | (h2o_abs(dqh) > H(FAST_PATH_MAX_DQ));
+        suspect = (t1 < L(FLAG_KAPPA_T) * mt) | (f1 < L(FLAG_KAPPA_F) * fbl) | (h2o_abs(dqh) > H(FAST_PATH_MAX_DQ));
 #endif
     }
 
@@ -789,7 +791,7 @@ H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], boo
         diag[6] = mx(ffx, ffy, ffz);
         diag[7] = gam * mx(in.vx, in.vy, in.vz);
         diag[8] = ml * mx(in.ax, in.ay, in.az);
-        diag[9] = L(fbz);
+        diag[9] = fbl;
         diag[10] = mx(F[0], F[1], F[2]);
         diag[11] = flag_kt; diag[12] = flag_kf; diag[13] = L(0);
     }
