@@ -185,6 +185,8 @@ static inline void cross3(const double a[3], const double b[3], double out[3])
     out[2] = a[0] * b[1] - a[1] * b[0];
 }
 
+static int g_warp_compat; /* defined below (Warp-twin deviations) */
+
 /* numba_hydrodynamics.py:53-105 (analyze_submersion_and_cob) */
 static double analyze_submersion_and_cob(const double wk[27][3], const double position[3],
                                          double cob[3])
@@ -205,7 +207,15 @@ static double analyze_submersion_and_cob(const double wk[27][3], const double po
     }
     memcpy(cob, position, 3 * sizeof(double));
     if (z_min >= 0) return 0.0; /* fully out */
-    if (z_max <= 0) return 1.0; /* fully in  */
+    if (z_max <= 0) {           /* fully in  */
+        if (g_warp_compat && submerged_count != 0) { /* C9: warp_hydrodynamics.py:57-58 */
+            const double inv_c = 1.0 / submerged_count;
+            cob[0] = sum_x * inv_c;
+            cob[1] = sum_y * inv_c;
+            cob[2] = sum_z * inv_c;
+        }
+        return 1.0;
+    }
     const double total_height = z_max - z_min;
     double ratio;
     if (total_height < 1e-6) {
@@ -329,9 +339,16 @@ static void calculate_lift(double speed, const double vel_dir[3], const double r
 }
 
 /* Behavioural deviations of the reference's Warp twin (warp_hydrodynamics.py, SURVEY.md
- * Appendix C), switchable so that the CUDA warp-compat mode has a checker too:
+ * Appendix C), switchable so that the CUDA warp-compat mode has a checker too.  Pinned against the
+ * reference's own kernel source executed through oracle/warp_shim (tests/golden/reference_warp_golden.npz):
  *   C1  accelerations are rotated FORWARD (quat_rotate) instead of by R^T (:216-217)
- *   C3  a dry body returns cob = cop = position instead of zeros (:59-61, :290) */
+ *   C3  a dry body returns cob = cop = position instead of zeros (:59-61, :290)
+ *   C4  flow along the body z axis: lift_dir is read without having been assigned (:196-200) -- reported
+ *       through reference_raises like the at-rest defect (A.8); the oracle returns zero lift there
+ *   C7  every rotation is wp.quat_rotate, x (2w^2 - 1) + 2 q (q.x) + 2 w (q x x), which is R(q) + 2 (|q|^2 - 1) I:
+ *       identical for unit quaternions, different for the un-normalised ones the Numba path accepts
+ *   C9  the centre of buoyancy is the mean of the strictly-wet keypoints whenever there is one (:57-58), also for
+ *       a fully submerged body (Numba returns p there, :97-98): differs when keypoints lie exactly on z = 0 */
 static int g_warp_compat = 0;
 ORACLE_API void oracle_set_warp_compat(int enable) { g_warp_compat = enable != 0; }
 
@@ -375,6 +392,13 @@ ORACLE_API void oracle_solve(const oracle_body_t *b, const double position[3],
     memset(out, 0, sizeof *out);
     double rot[3][3];
     quaternion_to_matrix(quat_xyzw, rot);
+    if (g_warp_compat) { /* C7: wp.quat_rotate == R(q) + 2 (|q|^2 - 1) I */
+        const double x = quat_xyzw[0], y = quat_xyzw[1], z = quat_xyzw[2], w = quat_xyzw[3];
+        const double d2 = 2.0 * (((x * x + y * y) + (z * z + w * w)) - 1.0);
+        rot[0][0] += d2;
+        rot[1][1] += d2;
+        rot[2][2] += d2;
+    }
     double wk[27][3];
     for (int i = 0; i < 27; ++i) {
         matvec3(rot, b->local_keypoints[i], wk[i]);
@@ -410,6 +434,12 @@ ORACLE_API void oracle_solve(const oracle_body_t *b, const double position[3],
                           out->drag_force, out->drag_torque);
     calculate_lift(speed, vel_dir, rot, area, b->water_density, b->lift_coefficient, sub_ratio,
                    out->lift_force);
+    if (g_warp_compat && speed > 1e-6) { /* C4: lift_dir unassigned when |v_hat x up| <= 1e-6 */
+        const double up[3] = {rot[0][2], rot[1][2], rot[2][2]};
+        double axis[3];
+        cross3(vel_dir, up, axis);
+        if (!(norm3(axis) > 1e-6)) out->reference_raises = 1;
+    }
     calculate_added_mass(sub_ratio, linear_accel, angular_accel, rot, b->added_mass_matrix,
                          out->added_mass_force, out->added_mass_torque);
     memcpy(out->center_of_buoyancy, cob, sizeof cob);

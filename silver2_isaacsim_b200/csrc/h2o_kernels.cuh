@@ -1117,7 +1117,8 @@ __global__ void __launch_bounds__(256) components_kernel(const __grid_constant__
     o[1] = wet ? S(double(r.py) + double(t.cop[1])) : S(0);
     o[2] = wet ? S(double(r.pz) + double(t.cop[2])) : S(0);
     reinterpret_cast<S*>(a.out_ratio)[i] = S(t.ratio);
-    if (a.out_flags) a.out_flags[i] = (wet && t.still) ? 1 : 0;
+    // bit 0: the reference raises / reads an unassigned variable here (A.8; in Warp-compat mode also C4)
+    if (a.out_flags) a.out_flags[i] = (t.ratio > 0.0 && (t.still || (a.warp_compat != 0 && t.lift_undefined))) ? 1 : 0;
 }
 
 // dtype conversion / packing helpers -----------------------------------------

@@ -247,8 +247,11 @@ template <typename H, typename L> struct BodyIn {
     // coefficient record (params.py COEFF_FIELDS) + globals
     L dimx, dimy, dimz;
     L c_drag, c_drag_ang, k_damp, k_damp_ang, c_am, c_am_ang, c_lift;
-    bool warp_compat;     // body_terms only: rotate accelerations FORWARD into the "body" frame, as the
-                          // reference's Warp twin does (warp_hydrodynamics.py:216-217)
+    bool warp_compat;     // body_terms only: the deviations of the reference's Warp twin (pinned by
+                          // tests/golden/reference_warp_golden.npz): accelerations rotated FORWARD into the "body"
+                          // frame (warp_hydrodynamics.py:216-217, C1); every rotation is wp.quat_rotate =
+                          // R(q) + 2 (|q|^2 - 1) I (C7); centre of buoyancy = mean of the wet keypoints also
+                          // for a fully submerged body (:57-58, C9)
     H rho_h, grav_h;      // globals: waterDensity, gravity (H for buoyancy)
     L rho;                // = L(rho_h)
     const L* am_dense;    // optional dense 6x6 added-mass matrix, row-major, body frame (the matrix
@@ -278,6 +281,9 @@ template <typename H, typename L> struct Terms {
     L tarm[3];            // (cop - p) x drag force, evaluated without cancellation
     uint32_t kp_mask;     // 27-bit submerged-keypoint mask (diagnostic)
     bool still;           // wet and speed <= 1e-6: the reference raises here
+    bool lift_undefined;  // moving, but the flow is along the body z axis: the Numba path returns zero lift
+                          // (numba_hydrodynamics.py:210-211), the Warp twin reads an unassigned lift_dir
+                          // (warp_hydrodynamics.py:196-200)
 };
 
 // ---- waterline: 27 keypoints {-hx,0,hx}x{hy,0,-hy}x{hz,0,-hz} against the plane z = 0
@@ -343,9 +349,11 @@ H2O_HD void body_terms(const BodyIn<H, L>& in, Terms<H, L>& t, const uint32_t* g
     const H hx2 = in.qx + in.qx, hy2 = in.qy + in.qy, hz2 = in.qz + in.qz;
     const H r20h = in.qx * hz2 - in.qw * hy2;
     const H r21h = in.qy * hz2 + in.qw * hx2;
-    const H r22h = H(1) - (in.qx * hx2 + in.qy * hy2);
     // |q|^2 - 1: the reference never normalises, so R is orthogonal only up to this.
     const H dqh = ((in.qx * in.qx + in.qy * in.qy) + (in.qz * in.qz + in.qw * in.qw)) - H(1);
+    // Warp twin: wp.quat_rotate(q, x) = x (2w^2 - 1) + 2 q_v (q_v.x) + 2w (q_v x x) = (R(q) + 2 dq I) x
+    const H diag_shift = in.warp_compat ? (dqh + dqh) : H(0);
+    const H r22h = (H(1) - (in.qx * hx2 + in.qy * hy2)) + diag_shift;
 
     const H dxh = H(in.dimx), dyh = H(in.dimy), dzh = H(in.dimz);
     Waterline<H> wl;
@@ -369,8 +377,9 @@ H2O_HD void body_terms(const BodyIn<H, L>& in, Terms<H, L>& t, const uint32_t* g
     const L xx = qx * x2, xy = qx * y2, xz = qx * z2;
     const L yy = qy * y2, yz = qy * z2, zz = qz * z2;
     const L wx = qw * x2, wy = qw * y2, wz = qw * z2;
-    const L r00 = L(1) - (yy + zz), r01 = xy - wz, r02 = xz + wy;
-    const L r10 = xy + wz, r11 = L(1) - (xx + zz), r12 = yz - wx;
+    const L dsh = L(diag_shift);
+    const L r00 = (L(1) - (yy + zz)) + dsh, r01 = xy - wz, r02 = xz + wy;
+    const L r10 = xy + wz, r11 = (L(1) - (xx + zz)) + dsh, r12 = yz - wx;
     const L r20 = L(r20h), r21 = L(r21h), r22 = L(r22h);
     const L dq = L(dqh);
 
@@ -383,7 +392,7 @@ H2O_HD void body_terms(const BodyIn<H, L>& in, Terms<H, L>& t, const uint32_t* g
 
     // ---- centre of buoyancy, body-relative: R * (h .* sum(sign)/count)
     const int cnt = h2o_popc(mask);
-    const L cinv = (partial && cnt > 0) ? h2o_rcp(L(cnt)) : L(0);
+    const L cinv = ((partial || (in.warp_compat && ratio > H(0))) && cnt > 0) ? h2o_rcp(L(cnt)) : L(0);
     const L csx = L(h2o_popc(mask & KP_XP) - h2o_popc(mask & KP_XN)) * (cinv * hx);
     const L csy = L(h2o_popc(mask & KP_YP) - h2o_popc(mask & KP_YN)) * (cinv * hy);
     const L csz = L(h2o_popc(mask & KP_ZP) - h2o_popc(mask & KP_ZN)) * (cinv * hz);
@@ -485,9 +494,11 @@ H2O_HD void body_terms(const BodyIn<H, L>& in, Terms<H, L>& t, const uint32_t* g
         const L ra = h2o_rsqrt(h2o_max(an2, L(1e-30)));
         const L an = h2o_sqrt_from_rsqrt(an2, ra);
         const bool ok = !(speed < L(1e-6)) && !(an < L(1e-6));
+        t.lift_undefined = !(speed < L(1e-6)) && (an < L(1e-6));
         const L dd = h2o_max(L(-1), h2o_min(L(1), -d2));
         // 1 - d^2 = |v_hat x up|^2 - (|up|^2 - 1),  |up|^2 - 1 = 4 dq (qx^2 + qy^2)
-        const L eta = L(4) * dq * (qx * qx + qy * qy);
+        // (Warp twin: up gains 2 dq e_z, so |up|^2 - 1 gains 2dq (2 r22 - 2dq))
+        const L eta = L(4) * dq * (qx * qx + qy * qy) + dsh * ((r22 + r22) - dsh);
         const L cl = lift_coefficient_of<kExactTrig>(dd, an2 - eta);
         const L mag = L(0.5) * in.rho * speed2 * cl * area * in.c_lift;
         const L s = ok ? mag * rl * ra : L(0);

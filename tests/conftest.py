@@ -25,6 +25,17 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_warp():
+    """Vectors produced by the reference's UNMODIFIED Warp kernel source (oracle/make_golden_warp.py)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "reference_warp_golden.npz"))
+    groups = {}
+    for key in z.files:
+        g, name = key.split("/")
+        groups.setdefault(g, {})[name] = z[key]
+    return groups
+
+
+@pytest.fixture(scope="session")
 def oracle():
     from oracle import hydro_oracle
 

@@ -101,6 +101,37 @@ def test_step_hexapod_table_and_robot_wrench(oracle, dev, dtype, kernel):
     assert (err <= tol + 1e-6).all(), float((err / (tol + 1e-6)).max())
 
 
+@pytest.mark.parametrize("every", [1, 5, 97], ids=["all_flagged", "every_5th", "every_97th"])
+@pytest.mark.parametrize("params", ["table", "per_body"])
+def test_flagged_bodies_with_robot_wrench(oracle, dev, every, params):
+    """fp32 mode, tile kernel, per-robot wrench: bodies the fast path flags (here: quaternions far from unit) are
+    re-evaluated in float64 at the end of their CTA and the robot sums are patched with the difference.
+    every = 1 overflows every CTA's deferred list (bitmap + end-of-CTA sweep); 5 fills it with ~30 bodies per tile
+    (list AND sweep); 97 stays inside the list (1 - 2 bodies per tile)."""
+    wl = W.hexapod_envs(1024 + 5) if params == "table" else W.sharded_robots(1024 + 5)
+    q = wl.quat_xyzw.astype(np.float64).copy()
+    q[::every] *= 1.0 + 3e-4                      # |q|^2 - 1 = 6e-4 >> FAST_PATH_MAX_DQ
+    wl.quat_xyzw = q.astype(np.float32)
+    ref = _ref(oracle, wl)
+    e = _engine(wl, torch.float32, dev, "tile", stats=True)
+    F, T, Wr = _run_step(e, wl, torch.float32, dev, "split", robot=True)
+    assert e.last_kernel == "tile"
+    _check(wl, torch.float32, ref, F, T, f"flagged every {every}")
+    want = oracle.robot_wrench(wl.pos, ref.force, ref.torque, wl.bodies_per_robot)
+    err, _ = scoring.vec_err(Wr, want)
+    mag = oracle.robot_wrench(wl.pos, np.abs(ref.force), np.abs(ref.torque), wl.bodies_per_robot)
+    tol = 1e-5 * np.abs(mag).max(axis=1) * 20
+    assert (err <= tol + 1e-6).all(), float((err / (tol + 1e-6)).max())
+    st = e.stats()
+    assert st["reevaluated_bodies"] >= (wl.n + every - 1) // every   # every marked body took the float64 path
+    # the engine-wide bitmap is clean again: an unflagged second step must not re-evaluate anything extra
+    wl2 = W.hexapod_envs(1024 + 5) if params == "table" else W.sharded_robots(1024 + 5)
+    e.stats(reset=True)
+    F2, T2, _ = _run_step(e, wl2, torch.float32, dev, "split", robot=True)
+    _check(wl2, torch.float32, _ref(oracle, wl2), F2, T2, "step after a flagged step")
+    assert e.stats()["reevaluated_bodies"] < 0.01 * wl2.n
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["fp32", "fp64"])
 @pytest.mark.parametrize("bpr", [1, 2, 4, 5, 7, 12, 32, 45])
 def test_robot_wrench_any_robot_size(oracle, dev, bpr, dtype):
@@ -767,6 +798,33 @@ def test_degenerate_inputs_stay_finite(dev):
     assert s["bodies"] == n and s["nonfinite_bodies"] == 1   # ... and is counted
     assert s["still_wet_bodies"] >= 5          # wet and at rest: where the reference raises TypeError
     assert (F[2].abs() <= 1e-5).all()          # zero mass: clamp scale = 0 * 500 / |F|
+
+
+@pytest.mark.parametrize("group", ["c2", "c3", "edge", "batched"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["fp32", "fp64"])
+def test_warp_compat_against_the_reference_warp_kernel(golden_warp, dev, group, dtype):
+    """f3 / a11: h2o_components in Warp-compat mode against vectors produced by the reference's own Warp kernel
+    source (tests/golden/reference_warp_golden.npz, oracle/make_golden_warp.py) -- every group incl. the edge
+    cases (un-normalised quaternions, faces exactly on the waterline), flags == the bodies for which that source
+    reads an unassigned variable."""
+    from silver2_isaacsim_b200 import HydroEngine
+    from tests.test_oracle_golden import warp_tolerance
+
+    d = golden_warp[group]
+    n = len(d["pos"])
+    ctor = np.broadcast_to(d["ctor"], (n, 12)) if d["ctor"].ndim == 1 else d["ctor"]
+    coeff = np.concatenate([ctor[:, 0:7], ctor[:, 9:12], np.ones((n, 1))], axis=1)
+    e = HydroEngine(n, dtype=dtype, device=dev, water_density=float(ctor[0, 7]), gravity=float(ctor[0, 8]))
+    e.set_params_per_body(coeff)
+    e.set_warp_compat(True)
+    out = e.components(*[_t(d[k], dtype, dev) for k in ("pos", "quat", "v", "w", "a", "al")], return_flags=True)
+    torch.cuda.synchronize()
+    assert (out[9].cpu().numpy().astype(bool) == d["raised"]).all()
+    ok = ~d["raised"]
+    for k, name in enumerate(NAMES):
+        x, y = out[k].double().cpu().numpy()[ok], d[name][ok].astype(np.float64)
+        err = np.abs(x - y).max(axis=1)
+        assert (err <= warp_tolerance(name, y)).all(), (group, name, float((err / warp_tolerance(name, y)).max()))
 
 
 def test_warp_compat_components(golden, oracle, dev):

@@ -81,6 +81,31 @@ def test_staged_bytecode_equals_live_tree(tmp_path):
     assert outs["live"].tobytes() == outs["staged"].tobytes()
 
 
+def test_warp_fixture_is_what_the_reference_warp_source_computes(golden_warp):
+    """tests/golden/reference_warp_golden.npz == the reference's Warp kernel source run now (through the shim or a
+    real ``warp``), bit for bit on a sample of every group; N launches of dim 1 == one launch of dim N."""
+    from oracle import ref_warp
+
+    if not ref_warp.available():
+        pytest.skip("reference tree not present")
+    for g in ("c2", "c3", "edge"):
+        d = golden_warp[g]
+        sel = np.arange(len(d["pos"]))[:: max(1, len(d["pos"]) // 64)]
+        out, raised = ref_warp.components_via_wrapper(d["ctor"][sel], d["pos"][sel], d["quat"][sel], d["v"][sel],
+                                                      d["w"][sel], d["a"][sel], d["al"][sel])
+        assert (raised == d["raised"][sel]).all()
+        for name in ref_warp.NAMES:
+            if ref_warp.load()[3] == "shim":
+                assert out[name].tobytes() == d[name][sel].tobytes(), (g, name)
+            else:  # a real warp: same source, Warp's own float32 code generation
+                np.testing.assert_allclose(out[name], d[name][sel], rtol=3e-5, atol=1e-5)
+    d = golden_warp["batched"]
+    b = ref_warp.components_batched(d["ctor"], d["pos"][:96], d["quat"][:96], d["v"][:96], d["w"][:96], d["a"][:96],
+                                    d["al"][:96])
+    for name in ref_warp.NAMES:
+        np.testing.assert_allclose(b[name], d[name][:96], rtol=3e-5, atol=1e-5)
+
+
 # --------------------------------------------------------------------------------------------- GPU
 @needs_ref
 @pytest.mark.gpu
