@@ -146,10 +146,14 @@ H2O_API int h2o_set_articulation_offsets(h2o_handle h, int64_t n_robots, const i
  * (hydrodynamics_behavior.py:194); the wrappers themselves take xyzw. */
 H2O_API int h2o_set_quat_order(h2o_handle h, int order);
 H2O_API int h2o_set_kernel(h2o_handle h, int choice);
-/* h2o_components only: reproduce the behavioural deviations of the reference's Warp twin
- * (warp_hydrodynamics.py): accelerations rotated forward instead of inverse
- * for the added-mass terms (:216-217) and cob = cop = position for a dry body (:59-61, :290).
- * Default 0 = the Numba semantics, which every other entry point always follows. */
+/* Follow the reference's WARP twin instead of its Numba path (warp_hydrodynamics.py; SURVEY.md Appendix C;
+ * pinned by tests/golden/reference_warp_golden.npz, vectors of the reference's own kernel source): accelerations
+ * rotated forward instead of inverse for the added-mass terms (:216-217), every rotation by wp.quat_rotate
+ * (= R(q) + 2(|q|^2 - 1) I for an un-normalised quaternion), centre of buoyancy = mean of the wet keypoints also
+ * when fully submerged (:57-58), cob = cop = position for a dry body (:59-61, :290).  Applies to h2o_components
+ * and to the fused step entry points (the production behaviour script evaluates forces through the Warp wrapper,
+ * hydrodynamics_behavior.py:19, :155); the step then runs every body through the float64 formulation on the
+ * per-body kernel (a compatibility mode, not a fast path).  Default 0 = the Numba semantics (north star). */
 H2O_API int h2o_set_warp_compat(h2o_handle h, int enable);
 /* fp32 mode only.  1 (default): every body meets the fp32-mode bound of the parity criterion (|dF|, |dtau| <=
  * max(1e-5 |.|_inf, 1e-6) against the float64 Numba path): the fused step flags the few bodies per 10 000 whose

@@ -21,10 +21,12 @@ Deliberate deviation: the reference script evaluates forces through its Warp wra
 (hydrodynamics_behavior.py:19, :155), whose kernel rotates the accelerations FORWARD into the
 "body" frame (warp_hydrodynamics.py:216-217) where the Numba path uses R^T
 (numba_hydrodynamics.py:229-230), so its linear added-mass force is -m R^2 a instead of -m a.
-BASELINE.json's north star pins this engine to the NUMBA semantics, and the fused step implements
-only those; for rotated bodies with a non-zero added-mass coefficient (Body: 0.2 / 0.1) the forces
-therefore differ from the Warp production path by that term.  The Warp
-deviations are available for A/B through ``HydroEngine.components`` with ``set_warp_compat(True)``.
+BASELINE.json's north star pins this engine to the NUMBA semantics, which the fused fast path
+implements; for rotated bodies with a non-zero added-mass coefficient (Body: 0.2 / 0.1) the forces
+therefore differ from the Warp production path by that term.
+``warp_compat=True`` switches the whole step (and ``HydroEngine.components``) to the Warp twin's
+semantics -- scored against the reference's own Warp kernel source, tests/golden/reference_warp_golden.npz --
+at the price of the per-body float64 kernel instead of the TMA tile kernel.
 """
 from __future__ import annotations
 
@@ -45,13 +47,15 @@ class BatchedHydrodynamicsBehavior:
 
     def __init__(self, prim_names: Sequence[str], view, device: str = "cuda:0",
                  config_path: Optional[str] = None, dtype: torch.dtype = torch.float32,
-                 bodies_per_robot: int = 0, robot_offsets: Optional[Sequence[int]] = None):
+                 bodies_per_robot: int = 0, robot_offsets: Optional[Sequence[int]] = None,
+                 warp_compat: bool = False):
         self.prim_names = list(prim_names)
         self._view = view
         self._device = device
         self._dtype = dtype
         self._config_path = config_path
         self._bodies_per_robot = int(bodies_per_robot)
+        self._warp_compat = bool(warp_compat)
         # robots of unequal size, e.g. [0, 19, 20] for one SILVER2 + the Obsea buoy (the main scene)
         self._robot_offsets = None if robot_offsets is None else [int(o) for o in robot_offsets]
         self._engine: Optional[HydroEngine] = None
@@ -104,6 +108,8 @@ class BatchedHydrodynamicsBehavior:
         self._engine = HydroEngine(n, dtype=self._dtype, device=self._device,
                                    water_density=first.waterDensity, gravity=first.gravity, quat_order="wxyz")
         self._engine.set_params_per_body(np.asarray(rows, dtype=np.float64))
+        if self._warp_compat:
+            self._engine.set_warp_compat(True)
         if self._robot_offsets is not None:
             self._engine.set_articulation_offsets(self._robot_offsets)
         else:

@@ -335,7 +335,7 @@ static int step_typed2(h2o_engine* e, StepArgs& a, cudaStream_t stream)
     if (e->kernel_choice == H2O_KERNEL_TILE) use_tile = true;
     else if (e->kernel_choice == H2O_KERNEL_AUTO) use_tile = a.n >= (long long)e->sm_count * 256;
     if (TB == 0 || !ptr_ok || a.n < TB) use_tile = false;
-    if (a.am_dense || a.surface_eta) use_tile = false;  // f4 generalisations: direct kernel (+ robot_wrench_kernel)
+    if (a.am_dense || a.surface_eta || a.warp_compat) use_tile = false;  // f3 / f4 modes: direct kernel (+ robot_wrench_kernel)
 
     long long done_bodies = 0;
     if (use_tile) {
@@ -456,6 +456,7 @@ static int step_device(h2o_engine* e, int layout, const void* pos, const void* q
     a.am_dense = e->am_dense; a.am_slot_type = e->am_slot_type; a.am_n_slots = e->am_slots;
     a.robot_offsets = e->robot_offsets; a.n_robots_var = e->n_robots_var;
     a.no_fallback = e->no_fallback;
+    a.warp_compat = e->warp_compat;
     a.redo_bitmap = e->redo_bitmap;
     a.surface_eta = e->surface_eta ? static_cast<const char*>(e->surface_eta) + size_t(first_body) * e->esz : nullptr;
     return e->dtype == H2O_F32 ? step_typed<float>(e, layout, a, stream) : step_typed<double>(e, layout, a, stream);
@@ -851,6 +852,7 @@ int h2o_set_warp_compat(h2o_handle h, int enable)
 {
     h2o_engine* e = check(h);
     if (!e) return H2O_ERR_BAD_HANDLE;
+    { DeviceGuard gi(e->device); invalidate_graph(e); }
     e->warp_compat = enable != 0;
     return H2O_OK;
 }

@@ -80,6 +80,8 @@ struct StepArgs {
     long long n_robots_var;
     uint32_t* redo_bitmap;   // one bit per body of the ENGINE (index first_body + i), all zero between launches:
                              // flagged bodies that found no slot in their CTA's deferred list
+    int warp_compat;         // 1: the fused step follows the reference's WARP twin instead of the
+                             // Numba path: every body through the float64 world-frame formulation, direct kernel only
     int no_fallback;         // study knob H2O_NO_FALLBACK: 1 = keep the fast-path result of flagged bodies,
                              // k = 2^j > 1 = re-evaluate exactly every k-th body instead (cost measurements)
 };
@@ -278,7 +280,7 @@ struct ExactStepOut {
 // Core (inlined into its two noinline carriers below): the fp64-mode arithmetic on one fp32-stored body.
 __device__ __forceinline__ ExactStepOut exact_eval_f32(const RawBody<float>& r, const float* c, int quat_wxyz, double rho,
                                                         double grav, double inv_dt, double surface_z, float cx, float cy,
-                                                        float cz, const float* am_dense)
+                                                        float cz, const float* am_dense, bool warp_compat = false)
 {
     BodyIn<double, double> g;
     g.pz = double(r.pz) - surface_z;
@@ -295,7 +297,7 @@ __device__ __forceinline__ ExactStepOut exact_eval_f32(const RawBody<float>& r, 
     g.dimx = c[0]; g.dimy = c[1]; g.dimz = c[2];
     g.c_drag = c[3]; g.c_drag_ang = c[4]; g.k_damp = c[5]; g.k_damp_ang = c[6];
     g.c_am = c[7]; g.c_am_ang = c[8]; g.c_lift = c[9];
-    g.warp_compat = false;
+    g.warp_compat = warp_compat;
     g.rho_h = rho; g.grav_h = grav; g.rho = double(float(rho));  // L constants as the fast path rounds them
     double md[36];
     g.am_dense = nullptr;
@@ -321,9 +323,9 @@ __device__ __forceinline__ ExactStepOut exact_eval_f32(const RawBody<float>& r, 
 // Persistent rollout kernel: the body's state lives in registers; handed over by reference (rare path).
 __device__ __noinline__ ExactStepOut body_step_exact_f32(const RawBody<float>& r, const float* c, int quat_wxyz, double rho,
                                                          double grav, double inv_dt, double surface_z, float cx, float cy,
-                                                         float cz)
+                                                         float cz, bool warp_compat = false)
 {
-    return exact_eval_f32(r, c, quat_wxyz, rho, grav, inv_dt, surface_z, cx, cy, cz, nullptr);
+    return exact_eval_f32(r, c, quat_wxyz, rho, grav, inv_dt, surface_z, cx, cy, cz, nullptr, warp_compat);
 }
 // Step kernels: re-read the flagged body's inputs from global memory (they are L2-resident: the tile was
 // streamed in microseconds ago), so the hot path keeps no input alive for this.  Scalars cross the call by
@@ -999,7 +1001,32 @@ __global__ void __launch_bounds__(256) step_direct_kernel(const __grid_constant_
             bin.am_dense = reinterpret_cast<const S*>(a.am_dense) + 36 * a.am_slot_type[(a.first_body + i) % a.am_n_slots];
         S F[3], T[3];
         uint32_t kp_mask;
-        step_one_body<S, kLayout, kParam, kStats, false>(a, i, bin, cl[10], env.surface_z, F, T, st, kp_mask);
+        bin.warp_compat = a.warp_compat != 0;  // fp64 mode: body_terms honours it
+        if (sizeof(S) == 4 && a.warp_compat) {
+            // fp32 mode, Warp-twin semantics: the float64 world-frame formulation for every body (compatibility
+            // mode, not a fast path: body_wrench_fast knows only the Numba semantics)
+            RawBody<float> rf;
+            rf.px = float(r.px); rf.py = float(r.py); rf.pz = float(r.pz);
+            rf.q0 = float(r.q0); rf.q1 = float(r.q1); rf.q2 = float(r.q2); rf.q3 = float(r.q3);
+            rf.vx = float(r.vx); rf.vy = float(r.vy); rf.vz = float(r.vz);
+            rf.wx = float(r.wx); rf.wy = float(r.wy); rf.wz = float(r.wz);
+            rf.pvx = float(r.pvx); rf.pvy = float(r.pvy); rf.pvz = float(r.pvz);
+            rf.pwx = float(r.pwx); rf.pwy = float(r.pwy); rf.pwz = float(r.pwz);
+            float cf[N_COEFF];
+#pragma unroll
+            for (int k = 0; k < N_COEFF; ++k) cf[k] = float(cl[k]);
+            const ExactStepOut o = body_step_exact_f32(rf, cf, a.quat_wxyz, a.rho, a.grav, a.inv_dt, env.surface_z,
+                                                       float(env.cx), float(env.cy), float(env.cz), true);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                F[k] = S(o.F[k]);
+                T[k] = S(o.T[k]);
+            }
+            if (kStats) accumulate_stats(st, double(F[0]), double(F[1]), double(F[2]), double(o.ratio), (o.flags & 1) != 0,
+                                         (o.flags & 2) != 0, true);
+        } else {
+            step_one_body<S, kLayout, kParam, kStats, false>(a, i, bin, cl[10], env.surface_z, F, T, st, kp_mask);
+        }
         S* of = reinterpret_cast<S*>(a.out_force) + 3 * i;
         S* ot = reinterpret_cast<S*>(a.out_torque) + 3 * i;
         of[0] = F[0]; of[1] = F[1]; of[2] = F[2];

@@ -471,6 +471,12 @@ H2O_HD void body_terms(const BodyIn<H, L>& in, Terms<H, L>& t, const uint32_t* g
         t.tarm[0] = psi * (rcx + k4 * (qx * urc + (gy * copz - gz * copy))) + px;
         t.tarm[1] = psi * (rcy + k4 * (qy * urc + (gz * copx - gx * copz))) + py;
         t.tarm[2] = psi * (rcz + k4 * (qz * urc + (gx * copy - gy * copx))) + pz;
+        if (in.warp_compat) {
+            // the factorisation above is for R(q); the Warp twin rotates with R(q) + 2 dq I: plain cross product
+            t.tarm[0] = copy * t.fd[2] - copz * t.fd[1];
+            t.tarm[1] = copz * t.fd[0] - copx * t.fd[2];
+            t.tarm[2] = copx * t.fd[1] - copy * t.fd[0];
+        }
     }
     {
         const L as2 = in.wx * in.wx + in.wy * in.wy + in.wz * in.wz;

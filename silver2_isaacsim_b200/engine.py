@@ -241,7 +241,8 @@ class HydroEngine:
         L.check(self._lib.h2o_set_kernel(self._h, code))
 
     def set_warp_compat(self, enable: bool = True):
-        """``components`` reproduces the deviations of the reference's Warp twin."""
+        """``components`` and the fused step follow the reference's Warp twin instead of the
+        Numba path; the step then runs on the per-body kernel in float64 (compatibility mode)."""
         L.check(self._lib.h2o_set_warp_compat(self._h, int(bool(enable))))
 
     def set_strict(self, enable: bool = True):

@@ -827,6 +827,36 @@ def test_warp_compat_against_the_reference_warp_kernel(golden_warp, dev, group, 
         assert (err <= warp_tolerance(name, y)).all(), (group, name, float((err / warp_tolerance(name, y)).max()))
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["fp32", "fp64"])
+def test_warp_compat_fused_step(oracle, dev, dtype):
+    """The fused step in Warp-compat mode (what the production behaviour script computes: Warp wrapper + the
+    behaviour tail) against the oracle with its Warp switch -- itself pinned to the reference's Warp kernel source
+    (tests/test_oracle_golden.py) -- incl. the per-robot wrench; switching back restores the Numba semantics."""
+    wl = W.sharded_robots(1500)
+    q = wl.quat_xyzw.astype(np.float64).copy()
+    q[::7] *= 1.0 + 2e-3                      # some un-normalised quaternions: quat_rotate != R(q) there
+    wl.quat_xyzw = q.astype(np.float32)
+    try:
+        oracle.set_warp_compat(True)
+        ref = _ref(oracle, wl)
+    finally:
+        oracle.set_warp_compat(False)
+    num = _ref(oracle, wl)
+    assert (np.abs(ref.force - num.force).max(axis=1) > 1e-3 * np.abs(num.force).max(axis=1)).mean() > 0.03
+    e = _engine(wl, dtype, dev)
+    e.set_warp_compat(True)
+    F, T, Wr = _run_step(e, wl, dtype, dev, "split", robot=True)
+    assert e.last_kernel == "direct"
+    _check(wl, dtype, ref, F, T, "warp-compat step")
+    want = oracle.robot_wrench(wl.pos, ref.force, ref.torque, wl.bodies_per_robot)
+    mag = oracle.robot_wrench(wl.pos, np.abs(ref.force), np.abs(ref.torque), wl.bodies_per_robot)
+    err, _ = scoring.vec_err(Wr, want)
+    assert (err <= (1e-5 if dtype == torch.float32 else 1e-11) * np.abs(mag).max(axis=1) * 20 + 1e-6).all()
+    e.set_warp_compat(False)
+    F, T, _ = _run_step(e, wl, dtype, dev, "split", robot=True)
+    _check(wl, dtype, num, F, T, "back to Numba semantics")
+
+
 def test_warp_compat_components(golden, oracle, dev):
     """f3: the components entry point can reproduce the Warp twin's deviations (forward rotation of
     the accelerations, cob = cop = p when dry); the default stays Numba semantics."""
