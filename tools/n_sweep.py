@@ -1,5 +1,6 @@
 """Fused step (C3 distribution, fp32, per-body records): time per step vs bodies per launch.
-Every size cycles through enough independent batches to exceed L2 several times; graph replay."""
+Every size cycles through enough independent batches to exceed L2 several times; graph replay.
+MIN_MS=500 keeps every size running for at least that long (the board's power-capped regime)."""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -23,6 +24,8 @@ for logn in (14, 16, 18, 19, 20, 21, 22, 24):
         e.bind(t(base.pos), t(base.quat_xyzw), t(base.lin_vel), t(base.ang_vel))
         es.append(e)
     reps = max(240, min(2000, int(2e9 // (168 * n))))
+    if float(os.environ.get("MIN_MS", "0")) > 0:  # sustained regime: at least MIN_MS of back-to-back replays per size
+        reps = max(reps, int(float(os.environ["MIN_MS"]) * 1e3 / max(3.0, 168 * n / 6.0e6)))
     per = nb * max(1, min(10, reps // nb)); reps = (reps // per) * per or per
     side = torch.cuda.Stream()
     with torch.cuda.stream(side):
