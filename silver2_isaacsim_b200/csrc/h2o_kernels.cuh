@@ -462,13 +462,13 @@ __device__ __noinline__ ExactStepOut combine_roles(const double* p)
 
 // fp32 mode: body-frame fast path (returns true when the body must be re-evaluated, see above);
 // fp64 mode: the world-frame formulation (exact in dq).
-template <typename S>
+template <typename S, bool kWarpSkip = false>
 __device__ __forceinline__ bool body_step(const BodyIn<double, S>& in, S mass, S F[3], S T[3], bool& clamped,
                                           bool& still, double& ratio, uint32_t& mask)
 {
     if (sizeof(S) == 4) {
         bool suspect;
-        body_wrench_fast<double, S>(in, mass, F, T, clamped, ratio, still, suspect, mask);
+        body_wrench_fast<double, S, kWarpSkip>(in, mass, F, T, clamped, ratio, still, suspect, mask);
         return suspect;
     } else {
         mask = 0;
@@ -501,13 +501,13 @@ __device__ __forceinline__ void accumulate_stats(ThreadStats& st, double fx, dou
 // One body of a step kernel: fast path + statistics.  Returns true when the body is flagged for the float64
 // re-evaluation; kDefer = false does it on the spot (redo_exact), kDefer = true leaves it to the caller.
 // `i` = body index inside the launch (a.pos etc. are the launch's base pointers).
-template <typename S, int kLayout, int kParam, bool kStats, bool kDefer>
+template <typename S, int kLayout, int kParam, bool kStats, bool kDefer, bool kWarpSkip = false>
 __device__ __forceinline__ bool step_one_body(const StepArgs& a, long long i, const BodyIn<double, S>& in, S mass,
                                               double surface_z, S F[3], S T[3], ThreadStats& st, uint32_t& mask)
 {
     bool clamped, still;
     double ratio;
-    bool redo = body_step<S>(in, mass, F, T, clamped, still, ratio, mask);
+    bool redo = body_step<S, kWarpSkip>(in, mass, F, T, clamped, still, ratio, mask);
     if (sizeof(S) == 4) {
         redo = redo && a.no_fallback != 1;
         if (a.no_fallback > 1) redo = ((a.first_body + i) & (long long)(a.no_fallback - 1)) == 0;  // study knob: every k-th body, k = 2^j
@@ -779,7 +779,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
                 BodyIn<double, S> bin;
                 make_body_in<S>(r, cl, a.quat_wxyz, a.rho, a.grav, inv_dt, env, bin);
                 uint32_t kp_mask;
-                if (step_one_body<S, kLayout, kParam, kStats, true>(a, tile_begin + tid, bin, cl[10], env.surface_z, F, T, st, kp_mask)) {
+                // robot mode (fleets: usually every body of a warp is fully submerged) skips the keypoint compares warp-wide;
+                // its CTAs run under a 96-register cap, the 80-register default kernel would spill on the branch
+                if (step_one_body<S, kLayout, kParam, kStats, true, kRobot>(a, tile_begin + tid, bin, cl[10], env.surface_z, F, T, st, kp_mask)) {
                     if (sizeof(S) == 4) {
                         const long long bi = tile_begin + tid;
                         const int slot = atomicAdd(redo_count, 1);

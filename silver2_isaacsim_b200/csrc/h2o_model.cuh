@@ -294,15 +294,33 @@ template <typename H> struct Waterline {
     uint32_t mask;   // 27-bit submerged-keypoint mask, bit layout kp_bit()
     H ratio;         // submersion ratio after the 1e-9 cut (numba_hydrodynamics.py:87, :277-279)
     bool partial;    // z_min < 0 < z_max: the centre of buoyancy is the mean of the wet keypoints
+    bool warp_needs_keypoints;  // kWarpSkip only: some lane of the warp is cut by the surface (warp-uniform)
 };
 // kMask = false: the caller already holds the mask (w.mask is left alone); only the ratio is formed
-template <typename H, bool kMask = true>
+// kWarpSkip (device, robot-mode tile kernels): when NO lane of the warp is cut by the surface -- a fleet walking on
+// the sea bed, the reference's main scene (SILVER2 at z = -18.4 m) -- every mask is all-or-nothing and the 27
+// compares are skipped for the whole warp.  Exact: ext is the largest keypoint offset bit for bit (same sums, same
+// association), rounding is monotone, so fl(pz + ext) < 0 implies t < -pz for every keypoint.  A top keypoint
+// exactly ON the surface (z_max == 0) is not wet and takes the compares.
+template <typename H, bool kMask = true, bool kWarpSkip = false>
 H2O_HD void waterline(H pz, H r20h, H r21h, H r22h, H dxh, H dyh, H dzh, Waterline<H>& w)
 {
     const H a = r20h * (dxh * H(0.5));
     const H b = r21h * (dyh * H(0.5));
     const H c = r22h * (dzh * H(0.5));
-    if (kMask) {
+    const H ext = (h2o_abs(a) + h2o_abs(b)) + h2o_abs(c);  // highest keypoint above p
+    const H z_min = pz - ext, z_max = pz + ext;
+    bool compare = kMask;
+    w.warp_needs_keypoints = true;
+#if defined(__CUDA_ARCH__)
+    if (kMask && kWarpSkip) {
+        const bool cut = !(z_max < H(0)) && !(z_min >= H(0));
+        compare = __any_sync(__activemask(), cut);
+        w.warp_needs_keypoints = compare;
+        if (!compare) w.mask = (z_max < H(0)) ? KP_ALL : 0u;
+    }
+#endif
+    if (compare) {
         const H abp = a + b, abm = a - b;
         const H m = -pz;  // keypoint wet  <=>  fl(t + pz) < 0  <=>  t < -pz  (exact)
         uint32_t mask = 0;
@@ -329,13 +347,13 @@ H2O_HD void waterline(H pz, H r20h, H r21h, H r22h, H dxh, H dyh, H dzh, Waterli
         h2o_or_if_less(mask, H(0), m, 1u << kp_bit(0, 0, 0));
         w.mask = mask;
     }
-    const H ext = (h2o_abs(a) + h2o_abs(b)) + h2o_abs(c);  // highest keypoint above p
-    const H z_min = pz - ext, z_max = pz + ext;
     const bool dry = z_min >= H(0);
     const bool partial = !dry && !(z_max <= H(0));
-    const H total_height = z_max - z_min;
     H ratio = H(1);
-    if (partial && !(total_height < H(1e-6))) ratio = h2o_min(H(1), -z_min * h2o_rcp_h(total_height));
+    if (!kWarpSkip || w.warp_needs_keypoints) {  // (no lane cut by the surface: every ratio is 0 or 1)
+        const H total_height = z_max - z_min;
+        if (partial && !(total_height < H(1e-6))) ratio = h2o_min(H(1), -z_min * h2o_rcp_h(total_height));
+    }
     if (dry || !(ratio > H(1e-9))) ratio = H(0);  // numba_hydrodynamics.py:87, :277-279
     w.ratio = ratio;
     w.partial = partial;
@@ -597,7 +615,7 @@ H2O_HD void net_wrench(const Terms<H, L>& t, L mass, L F[3], L T[3], bool& clamp
 // fp64 mode, which keeps the world-frame formulation above.  The one place where dq matters
 // even in fp32 (the cancelling cop x F_d, see body_terms) keeps its first-order dq term.
 // ---------------------------------------------------------------------------
-template <typename H, typename L>
+template <typename H, typename L, bool kWarpSkip = false>
 H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], bool& clamped, H& ratio_out,
                              bool& still, bool& suspect, uint32_t& mask_out, L* diag = nullptr)
 {
@@ -612,7 +630,7 @@ H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], boo
     const H dqh = ((in.qx * in.qx + in.qy * in.qy) + (in.qz * in.qz + in.qw * in.qw)) - H(1);
     const H dxh = H(in.dimx), dyh = H(in.dimy), dzh = H(in.dimz);
     Waterline<H> wl;
-    waterline<H>(in.pz, r20h, r21h, r22h, dxh, dyh, dzh, wl);
+    waterline<H, true, kWarpSkip>(in.pz, r20h, r21h, r22h, dxh, dyh, dzh, wl);
     const uint32_t mask = wl.mask;
     const H ratio = wl.ratio;
     const bool partial = wl.partial;
@@ -635,18 +653,21 @@ H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], boo
     const L vol = in.dimx * ayz;
 
     // ---- centre of buoyancy in the body frame: h .* sum(sign)/count
-    const int cnt = h2o_popc(mask);
-    const L cinv = (partial && cnt > 0) ? h2o_rcp(L(cnt)) : L(0);
-    const L chalf = cinv * L(0.5);
-    const L cbx = L(h2o_popc(mask & KP_XP) - h2o_popc(mask & KP_XN)) * (chalf * in.dimx);
-    const L cby = L(h2o_popc(mask & KP_YP) - h2o_popc(mask & KP_YN)) * (chalf * in.dimy);
-    const L cbz = L(h2o_popc(mask & KP_ZP) - h2o_popc(mask & KP_ZN)) * (chalf * in.dimz);
+    L cinv = L(0), cbx = L(0), cby = L(0), cbz = L(0);
+    if (!kWarpSkip || wl.warp_needs_keypoints) {  // no lane cut by the surface: cob = p in every lane
+        const int cnt = h2o_popc(mask);
+        cinv = (partial && cnt > 0) ? h2o_rcp(L(cnt)) : L(0);
+        const L chalf = cinv * L(0.5);
+        cbx = L(h2o_popc(mask & KP_XP) - h2o_popc(mask & KP_XN)) * (chalf * in.dimx);
+        cby = L(h2o_popc(mask & KP_YP) - h2o_popc(mask & KP_YN)) * (chalf * in.dimy);
+        cbz = L(h2o_popc(mask & KP_ZP) - h2o_popc(mask & KP_ZN)) * (chalf * in.dimz);
+    }
     // Buoyancy torque (cob - p) x (0,0,fb) needs the horizontal offset of the centre of buoyancy,
     // which vanishes at hydrostatic equilibrium as a difference of O(h) terms: rows 0,1 of R and
     // the weighted sum are carried in H so that the restoring torque of a floating body keeps
     // its relative accuracy (a floating buoy sits exactly in that regime).
-    L tbuoy_x, tbuoy_y;
-    {
+    L tbuoy_x = L(0), tbuoy_y = L(0);
+    if (!kWarpSkip || wl.warp_needs_keypoints) {  // no lane cut by the surface: cinv = 0 in every lane, the arm is zero
         const H sxh = H(h2o_popc(mask & KP_XP) - h2o_popc(mask & KP_XN)) * (dxh * H(0.5));
         const H syh = H(h2o_popc(mask & KP_YP) - h2o_popc(mask & KP_YN)) * (dyh * H(0.5));
         const H szh = H(h2o_popc(mask & KP_ZP) - h2o_popc(mask & KP_ZN)) * (dzh * H(0.5));
@@ -681,10 +702,16 @@ H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], boo
 #endif
 
     // ---- projected area, centre of pressure (body frame) -- see body_terms
-    const uint32_t f0 = (d0 < L(0)) ? (1u << kp_bit(1, 0, 0)) : (1u << kp_bit(-1, 0, 0));
-    const uint32_t f1 = (d1 < L(0)) ? (1u << kp_bit(0, 1, 0)) : (1u << kp_bit(0, -1, 0));
-    const uint32_t f2 = (d2 < L(0)) ? (1u << kp_bit(0, 0, 1)) : (1u << kp_bit(0, 0, -1));
-    const L w0 = (mask & f0) ? L(1) : L(0), w1 = (mask & f1) ? L(1) : L(0), w2 = (mask & f2) ? L(1) : L(0);
+    L w0, w1, w2;
+    const bool per_face = !kWarpSkip || wl.warp_needs_keypoints;  // warp-uniform
+    if (per_face) {
+        const uint32_t f0 = (d0 < L(0)) ? (1u << kp_bit(1, 0, 0)) : (1u << kp_bit(-1, 0, 0));
+        const uint32_t f1 = (d1 < L(0)) ? (1u << kp_bit(0, 1, 0)) : (1u << kp_bit(0, -1, 0));
+        const uint32_t f2 = (d2 < L(0)) ? (1u << kp_bit(0, 0, 1)) : (1u << kp_bit(0, 0, -1));
+        w0 = (mask & f0) ? L(1) : L(0); w1 = (mask & f1) ? L(1) : L(0); w2 = (mask & f2) ? L(1) : L(0);
+    } else {  // no lane cut by the surface: every face of a body is wet, or none
+        w0 = w1 = w2 = mask ? L(1) : L(0);
+    }
     const L g0 = w0 * d0, g1 = w1 * d1, g2 = w2 * d2;
     const L area = (h2o_abs(g0) * ayz + h2o_abs(g1) * axz) + h2o_abs(g2) * axy;
     const bool faces = area > L(1e-6);
@@ -705,9 +732,12 @@ H2O_HD void body_wrench_fast(const BodyIn<H, L>& in, L mass, L F[3], L T[3], boo
     const L uu = qx * qx + qy * qy + qz * qz;
     const L gbx = qx * udd - uu * d0, gby = qy * udd - uu * d1, gbz = qz * udd - uu * d2;
     const L nf = faces ? L(0) : L(1);
-    const L tdx = (gd1 * d2) * (w1 - w2) + k4 * (gby * s2 - gbz * s1) + nf * (d1 * cbz - d2 * cby);
-    const L tdy = (gd2 * d0) * (w2 - w0) + k4 * (gbz * s0 - gbx * s2) + nf * (d2 * cbx - d0 * cbz);
-    const L tdz = (gd0 * d1) * (w0 - w1) + k4 * (gbx * s1 - gby * s0) + nf * (d0 * cby - d1 * cbx);
+    L tdx = k4 * (gby * s2 - gbz * s1), tdy = k4 * (gbz * s0 - gbx * s2), tdz = k4 * (gbx * s1 - gby * s0);
+    if (per_face) {  // (otherwise w0 = w1 = w2 and cob = p: both groups are exactly zero)
+        tdx = (gd1 * d2) * (w1 - w2) + tdx + nf * (d1 * cbz - d2 * cby);
+        tdy = (gd2 * d0) * (w2 - w0) + tdy + nf * (d2 * cbx - d0 * cbz);
+        tdz = (gd0 * d1) * (w0 - w1) + tdz + nf * (d0 * cby - d1 * cbx);
+    }
     // running sum of the torque groups' magnitudes (conditioning check at the end)
     L mt = h2o_abs(psi) * ((h2o_abs(tdx) + h2o_abs(tdy)) + h2o_abs(tdz));
 

@@ -33,7 +33,12 @@ def run(es, per, rounds=31):
 res = {}
 es = engines(lambda b: W.heterogeneous_boxes(1 << 20, seed=100 + b), 6, False); res["c3_1M"] = run(es, 24); del es
 es = engines(lambda b: W.sharded_robots(110592, seed=200 + b), 2, True); res["c4_shard"] = run(es, 10); del es
+def deep(wl):
+    wl.pos[:, 2] -= 2.0   # every body below the surface: a fleet on the sea bed (the reference scene sits at -18.4 m)
+    return wl
+es = engines(lambda b: deep(W.sharded_robots(110592, seed=200 + b)), 2, True); res["c4_deep"] = run(es, 10); del es
 es = engines(lambda b: W.hexapod_envs(4096, seed=300 + b), 1, True); res["c2"] = run(es, 200); del es
+es = engines(lambda b: deep(W.hexapod_envs(4096, seed=300 + b)), 1, True); res["c2_deep"] = run(es, 200); del es
 es = engines(lambda b: W.heterogeneous_boxes(1 << 18, seed=400 + b), 24, False); res["c3_256k"] = run(es, 48); del es
 print(json.dumps(res))
 ''' % ROOT
