@@ -133,6 +133,43 @@ def test_flagged_bodies_with_robot_wrench(oracle, dev, every, params):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["fp32", "fp64"])
+def test_robot_tiles_with_uniform_and_mixed_warps(oracle, dev, dtype):
+    """Robot-mode tile kernels skip the keypoint compares (and what hangs on them) for warps in which no lane is cut
+    by the surface.  Tiles of 152 bodies built so that every case occurs: whole tiles deep under water / dry, one cut
+    lane in an otherwise deep warp, deep and dry lanes mixed (no cut lane: skipped, masks all-or-nothing per lane),
+    and bodies whose TOP face lies exactly on z = 0 (identity quaternion, p_z = -h_z: fully submerged by z_max <= 0,
+    but the top keypoints are not wet -- such a lane must take the compares)."""
+    wl = W.sharded_robots(8 * 12)                       # 12 tiles of 8 robots
+    z = wl.pos[:, 2].astype(np.float64)
+    tile = np.arange(wl.n) // 152
+    lane = np.arange(wl.n) % 152
+    z[tile == 0] = -5.0 - 0.01 * lane[tile == 0]          # deep
+    z[tile == 1] = 5.0 + 0.01 * lane[tile == 1]           # dry
+    z[tile == 2] = -5.0
+    z[(tile == 2) & (lane == 40)] = 0.01                  # one cut lane in warp 1
+    z[tile == 3] = np.where(lane[tile == 3] % 2 == 0, -5.0, 5.0)   # deep / dry alternating: no lane cut
+    z[tile == 4] = -5.0
+    top = (tile == 4) & (lane % 9 == 0)                   # top face exactly on the surface
+    wl.quat_xyzw[top] = np.array([0, 0, 0, 1], dtype=np.float32)
+    z[top] = -0.5 * wl.coeff[top, 2].astype(np.float64)   # -h_z, exact in fp32 (a halved fp32 number)
+    z[tile == 5] = -5.0
+    wl.quat_xyzw[(tile == 5) & (lane % 5 == 0)] *= np.float32(1.001)  # flagged lanes inside skipped warps
+    wl.pos[:, 2] = z.astype(np.float32)
+    ref = _ref(oracle, wl)
+    e = _engine(wl, dtype, dev, "tile", stats=True)
+    F, T, Wr = _run_step(e, wl, dtype, dev, "split", robot=True)
+    assert e.last_kernel == "tile"
+    _check(wl, dtype, ref, F, T, "uniform / mixed warps")
+    assert (F[tile == 1] == 0).all() and (T[tile == 1] == 0).all()
+    want = oracle.robot_wrench(wl.pos, ref.force, ref.torque, wl.bodies_per_robot)
+    mag = oracle.robot_wrench(wl.pos, np.abs(ref.force), np.abs(ref.torque), wl.bodies_per_robot)
+    err, _ = scoring.vec_err(Wr, want)
+    assert (err <= (1e-5 if dtype == torch.float32 else 1e-11) * np.abs(mag).max(axis=1) * 20 + 1e-6).all()
+    st = e.stats()
+    assert st["wet_bodies"] == float((ref.components["sub_ratio"] > 0).sum())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["fp32", "fp64"])
 @pytest.mark.parametrize("bpr", [1, 2, 4, 5, 7, 12, 32, 45])
 def test_robot_wrench_any_robot_size(oracle, dev, bpr, dtype):
     """The 19-body hexapod has a compiled-in robot size; every other size takes the run-time path
