@@ -30,6 +30,12 @@
 
 #include "h2o_model.cuh"
 
+// study knob (-DH2O_SKIP_ALL=true): the warp-uniform surface-logic skip of the robot-mode kernels in EVERY tile kernel
+// (the 80-register default kernel spills on it; used with regime-sorted inputs to bound what an in-tile sort could give)
+#ifndef H2O_SKIP_ALL
+#define H2O_SKIP_ALL false
+#endif
+
 namespace h2o {
 
 enum : int { LAYOUT_SPLIT = 0, LAYOUT_PHYSX = 1, LAYOUT_VIEW = 2 };
@@ -781,7 +787,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) step_tile_kernel(const _
                 uint32_t kp_mask;
                 // robot mode (fleets: usually every body of a warp is fully submerged) skips the keypoint compares warp-wide;
                 // its CTAs run under a 96-register cap, the 80-register default kernel would spill on the branch
-                if (step_one_body<S, kLayout, kParam, kStats, true, kRobot>(a, tile_begin + tid, bin, cl[10], env.surface_z, F, T, st, kp_mask)) {
+                if (step_one_body<S, kLayout, kParam, kStats, true, (kRobot || H2O_SKIP_ALL)>(a, tile_begin + tid, bin, cl[10], env.surface_z, F, T, st, kp_mask)) {
                     if (sizeof(S) == 4) {
                         const long long bi = tile_begin + tid;
                         const int slot = atomicAdd(redo_count, 1);
